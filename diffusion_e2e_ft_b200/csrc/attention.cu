@@ -1,0 +1,323 @@
+// Flash attention for head_dim 64 on sm_100a: softmax(Q K^T * scale) V, no mask.
+//
+// Warp-specialised: warp0 = TMA producer (Q once, K/V tiles through a 4-stage smem ring),
+// warp1 = tcgen05 issuer, warps 2..5 = softmax (one query row per thread — the TMEM lane layout
+// gives each thread its own row, so row max / row sum need no shuffles).
+//   S_j = Q K_j^T        tcgen05.mma  M128 N128 K64   -> TMEM (double buffered)
+//   P_j = exp2(S_j*c - m_j*c)  fp32 in registers -> fp16 into smem (SWIZZLE_128B, K-major A operand)
+//   T_j = P_j V_j        tcgen05.mma  M128 N64  K128  -> TMEM (double buffered), V consumed
+//                        MN-major straight from its [keys x d] TMA tile (no transpose)
+//   O   = O*alpha_j + T_j in registers (fp32), one tile late so it overlaps the next S/P.
+// Joint attention (GeoWizard): kv_segments = 2 walks the K/V tiles of batch b%(B/2) then
+// b%(B/2)+B/2 — the concatenated K/V of attention.py:482-491 is never materialised.
+#include "common.cuh"
+#include "../../include/b200_e2eft.h"
+
+namespace b200 {
+
+constexpr int kAttThreads = 192;
+constexpr int kBq = 128;    // query rows per CTA
+constexpr int kBk = 128;    // keys per tile
+constexpr int kD = 64;
+constexpr int kKvStages = 4;
+constexpr int kTileBytes = kBk * kD * 2;      // 16 KB (Q, K, V tiles)
+constexpr int kPBytes = kBq * kBk * 2;        // 32 KB
+constexpr int kAttSmem = kTileBytes + kKvStages * 2 * kTileBytes + 2 * kPBytes + 1024 + 1024;
+
+struct AttParams {
+  int B, heads, Lq, Lk, kv_segments;
+  float scale_log2;
+  __half* out;
+  long long o_bs, o_ls;
+};
+
+__global__ void __launch_bounds__(kAttThreads, 1)
+attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + kKvStages * kTileBytes;
+  uint8_t* sP = sV + kKvStages * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + kKvStages;
+  uint64_t* kv_empty = v_full + kKvStages;
+  uint64_t* s_full = kv_empty + kKvStages;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBq;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int tiles_per_seg = (p.Lk + kBk - 1) / kBk;
+  const int n_tiles = tiles_per_seg * p.kv_segments;
+  const int half_b = p.kv_segments == 2 ? p.B / 2 : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tS = tmem_base;            // S0: [0,128)  S1: [128,256)
+  const uint32_t tO = tmem_base + 256;      // T0: [256,320) T1: [320,384)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_3d(&tmQ, q_full, sQ, h * kD, q0, b, kEvictFirst);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int seg = 0; seg < p.kv_segments; ++seg) {
+        const int kb = p.kv_segments == 2 ? (b % half_b) + seg * half_b : b;
+        for (int j = 0; j < tiles_per_seg; ++j) {
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&k_full[stage], kTileBytes);
+          tma_load_3d(&tmK, &k_full[stage], sK + stage * kTileBytes, h * kD, j * kBk, kb, kEvictLast);
+          mbar_arrive_expect_tx(&v_full[stage], kTileBytes);
+          tma_load_3d(&tmV, &v_full[stage], sV + stage * kTileBytes, h * kD, j * kBk, kb, kEvictLast);
+          if (++stage == kKvStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_qk = make_idesc_f16(kBq, kBk, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_f16(kBq, kD, 0, 1);   // B (=V) is MN-major
+    mbar_wait(q_full, 0);
+    const uint64_t qdesc = make_desc_sw128(smem_u32(sQ), 16, 1024);
+    auto issue_qk = [&](int j) {
+      const int st = j % kKvStages;
+      mbar_wait(&k_full[st], (j / kKvStages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t kdesc = make_desc_sw128(smem_u32(sK + st * kTileBytes), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_f16(tS + (j & 1) * kBk, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[j & 1]);
+      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) issue_qk(j + 1);
+      const int st = j % kKvStages;
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&v_full[st], (j / kKvStages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t pbase = smem_u32(sP + (j & 1) * kPBytes);
+        const uint32_t vbase = smem_u32(sV + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kBk / 16; ++k) {
+          // A = P[:, 16k..16k+16): K-major, two 64-key swizzle atoms of 16 KB each
+          const uint64_t pdesc = make_desc_sw128(pbase + (k >> 2) * (kBq * 128) + (k & 3) * 32, 16, 1024);
+          // B = V[16k..16k+16, :]: MN-major, 16 key rows = 2 groups of 8 rows (SBO = 1024 B)
+          const uint64_t vdesc = make_desc_sw128(vbase + k * 2048, 16, 1024);
+          umma_f16(tO + (j & 1) * kD, pdesc, vdesc, idesc_pv, k != 0);
+        }
+        umma_commit(&o_full[j & 1]);
+        umma_commit(&kv_empty[st]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / output warps
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float o[kD];
+#pragma unroll
+    for (int i = 0; i < kD; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    const float c = p.scale_log2;
+    uint8_t* prow0 = sP + row * 128;
+    const int sw = row & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int jj = j % tiles_per_seg;
+      const int valid = min(kBk, p.Lk - jj * kBk);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tS + (j & 1) * kBk + lane_off;
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < kBk; cc += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(ts + cc, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float v = (cc + e < valid) ? __uint_as_float(r[e]) : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f((m - m_new) * c);
+      const float mc = m_new * c;
+      // pass 2: probabilities -> smem (fp16), row sum
+      float rs = 0.f;
+      uint8_t* prow = prow0 + (j & 1) * kPBytes;
+#pragma unroll 1
+      for (int cc = 0; cc < kBk; cc += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(ts + cc, r);
+        tmem_ld_wait();
+        uint8_t* pchunk = prow + (cc >> 6) * (kBq * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i0 = g * 8 + e * 2;
+            float p0 = (cc + i0 < valid) ? exp2f(__uint_as_float(r[i0]) * c - mc) : 0.f;
+            float p1 = (cc + i0 + 1 < valid) ? exp2f(__uint_as_float(r[i0 + 1]) * c - mc) : 0.f;
+            __half2 hh = __floats2half2_rn(p0, p1);
+            // accumulate the rounded values so the normaliser matches what the MMA consumes
+            float2 back = __half22float2(hh);
+            rs += back.x + back.y;
+            pk[e] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          const int chunk16 = ((cc & 63) >> 3) + g;      // logical 16-byte chunk within the 128-B row
+          *reinterpret_cast<uint4*>(pchunk + ((chunk16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      l = l * alpha + rs;
+      m = m_new;
+      tc_fence_before();          // our TMEM reads of S are done before the MMA warp may overwrite it
+      fence_proxy_async_smem();   // P visible to the tensor-core (async) proxy
+      mbar_arrive(&p_full[j & 1]);
+
+      if (j > 0) {
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t to = tO + ((j - 1) & 1) * kD + lane_off;
+#pragma unroll
+        for (int cc = 0; cc < kD; cc += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(to + cc, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[cc + e] = o[cc + e] * alpha_prev + __uint_as_float(r[e]);
+        }
+      }
+      alpha_prev = alpha;
+    }
+    {
+      const int j = n_tiles - 1;
+      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t to = tO + (j & 1) * kD + lane_off;
+#pragma unroll
+      for (int cc = 0; cc < kD; cc += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(to + cc, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[cc + e] = o[cc + e] * alpha_prev + __uint_as_float(r[e]);
+      }
+    }
+    const int qrow = q0 + row;
+    if (qrow < p.Lq) {
+      const float inv = 1.0f / l;
+      __half* dst = p.out + (long long)b * p.o_bs + (long long)qrow * p.o_ls + h * kD;
+#pragma unroll
+      for (int g = 0; g < kD; g += 8) {
+        __half2 h0 = __floats2half2_rn(o[g] * inv, o[g + 1] * inv);
+        __half2 h1 = __floats2half2_rn(o[g + 2] * inv, o[g + 3] * inv);
+        __half2 h2 = __floats2half2_rn(o[g + 4] * inv, o[g + 5] * inv);
+        __half2 h3 = __floats2half2_rn(o[g + 6] * inv, o[g + 7] * inv);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + g) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_attention_d64(const void* q, long long q_bs, long long q_ls, const void* k,
+                                  long long k_bs, long long k_ls, const void* v, long long v_bs,
+                                  long long v_ls, void* out, long long o_bs, long long o_ls, int B,
+                                  int heads, int Lq, int Lk, int kv_segments, float scale,
+                                  void* stream) {
+  B200_CHECK_ARG(q && k && v && out, "b200_attention_d64: null pointer");
+  B200_CHECK_ARG(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "b200_attention_d64: bad shape");
+  B200_CHECK_ARG(kv_segments == 1 || (kv_segments == 2 && B % 2 == 0), "b200_attention_d64: kv_segments=%d B=%d", kv_segments, B);
+  B200_CHECK_ARG(q_ls % 8 == 0 && k_ls % 8 == 0 && v_ls % 8 == 0 && o_ls % 8 == 0 && q_bs % 8 == 0 &&
+                     k_bs % 8 == 0 && v_bs % 8 == 0 && o_bs % 8 == 0,
+                 "b200_attention_d64: strides must be multiples of 8 elements");
+  B200_CHECK_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0,
+                 "b200_attention_d64: pointers must be 16-byte aligned");
+  CUtensorMap tq, tk, tv;
+  const uint32_t box[3] = {kD, kBq, 1};
+  {
+    uint64_t dims[3] = {(uint64_t)heads * kD, (uint64_t)Lq, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)q_ls * 2, (uint64_t)q_bs * 2};
+    int r = encode_tmap(&tq, q, 3, dims, str, box, nullptr);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)heads * kD, (uint64_t)Lk, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)k_ls * 2, (uint64_t)k_bs * 2};
+    int r = encode_tmap(&tk, k, 3, dims, str, box, nullptr);
+    if (r) return r;
+    uint64_t strv[2] = {(uint64_t)v_ls * 2, (uint64_t)v_bs * 2};
+    r = encode_tmap(&tv, v, 3, dims, strv, box, nullptr);
+    if (r) return r;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(attention smem=%d): %s", kAttSmem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  AttParams p;
+  p.B = B; p.heads = heads; p.Lq = Lq; p.Lk = Lk; p.kv_segments = kv_segments;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = (__half*)out; p.o_bs = o_bs; p.o_ls = o_ls;
+  dim3 grid((Lq + kBq - 1) / kBq, heads, B);
+  attention_d64_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  B200_CHECK_LAUNCH("attention_d64_kernel");
+  return 0;
+}

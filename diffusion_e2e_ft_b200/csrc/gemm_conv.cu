@@ -1,0 +1,292 @@
+// Host side of the tcgen05 GEMM / implicit-GEMM conv: tensor-map construction, tile-shape
+// selection, launch.  C-ABI entry points are declared in include/b200_e2eft.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "gemm_conv.cuh"
+#include "../../include/b200_e2eft.h"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                CUtensorMapDataType dtype) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return -2;
+  }
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    e[i] = elem_strides ? elem_strides[i] : 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(gptr), d, s, b, e,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error(
+        "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] strides [%llu %llu %llu] "
+        "box [%u %u %u %u] ptr %p",
+        (int)r, rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
+        (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0),
+        (unsigned long long)s[0], (unsigned long long)(rank > 2 ? s[1] : 0),
+        (unsigned long long)(rank > 3 ? s[2] : 0), b[0], rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0,
+        rank > 3 ? b[3] : 0, gptr);
+    return -3;
+  }
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+template <int BN, typename OutT>
+static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
+                      const GemmParams& p, cudaStream_t st) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  auto kern = gemm_conv_kernel<BN, OutT>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(smem=%d): %s", S::kTotalBytes, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  int tiles = p.batch * p.m_tiles * p.n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, S::kTotalBytes, st>>>(a, a2, b, p);
+  B200_CHECK_LAUNCH("gemm_conv_kernel");
+  return 0;
+}
+
+template <typename OutT>
+static int launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
+                     const GemmParams& p, cudaStream_t st) {
+  switch (bn) {
+    case 32: return launch_one<32, OutT>(a, a2, b, p, st);
+    case 64: return launch_one<64, OutT>(a, a2, b, p, st);
+    case 128: return launch_one<128, OutT>(a, a2, b, p, st);
+    case 160: return launch_one<160, OutT>(a, a2, b, p, st);
+    case 256: return launch_one<256, OutT>(a, a2, b, p, st);
+  }
+  set_last_error("unsupported BLOCK_N %d", bn);
+  return -1;
+}
+
+// Pick BLOCK_N: minimise (waves x per-tile cost).  Per-tile cost ~ BLOCK_N MMA columns + fixed
+// epilogue/prologue overhead.  GEGLU needs value|gate halves, any of the sizes works (even).
+static int pick_block_n(int N, long long m_tiles_total, int force) {
+  if (force) return force;
+  const int cands[5] = {256, 160, 128, 64, 32};
+  int best = 32;
+  double best_cost = 1e30;
+  for (int i = 0; i < 5; ++i) {
+    int bn = cands[i];
+    long long n_tiles = (N + bn - 1) / bn;
+    long long tiles = n_tiles * m_tiles_total;
+    long long waves = (tiles + sm_count() - 1) / sm_count();
+    double cost = (double)waves * (bn + 24.0);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static int g_force_bn = 0;
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" const char* b200_last_error_string(void) { return b200::last_error(); }
+extern "C" void b200_debug_force_block_n(int bn) { b200::g_force_bn = bn; }
+extern "C" int b200_abi_version(void) { return 1; }
+
+extern "C" int b200_linear(const void* A, long long lda, long long a_batch_stride, const void* W,
+                           long long ldw, long long w_batch_stride, int M, int N, int K, int batch,
+                           const float* bias, int bias_row, const void* residual, long long ld_res,
+                           long long res_batch_stride, void* out, long long ldo,
+                           long long out_batch_stride, int out_f32, int act, float alpha,
+                           void* stream) {
+  B200_CHECK_ARG(A && W && out, "b200_linear: null pointer");
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "b200_linear: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
+  B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "b200_linear: lda/ldw must be multiples of 8 elements (16 B)");
+  B200_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                 "b200_linear: pointers must be 16-byte aligned");
+  B200_CHECK_ARG(ldo % 8 == 0 || N % 8 != 0, "b200_linear: ldo must be a multiple of 8");
+  B200_CHECK_ARG(act != ACT_GEGLU || (N % 16 == 0 && bias), "b200_linear: GEGLU needs bias and N%%16==0");
+  B200_CHECK_ARG(batch == 1 || (a_batch_stride % 8 == 0 && (w_batch_stride % 8 == 0)),
+                 "b200_linear: batch strides must be multiples of 8 elements");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N;
+  p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  p.batch = batch;
+  p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.b_batched = (w_batch_stride != 0 && batch > 1);
+  int bn = pick_block_n(N, (long long)p.m_tiles * batch, g_force_bn);
+  if (act == ACT_GEGLU) bn = (N % 160 == 0 && g_force_bn == 0) ? 160 : (N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 0));
+  B200_CHECK_ARG(bn != 0, "b200_linear: GEGLU N=%d not tileable", N);
+  p.n_tiles = (N + bn - 1) / bn;
+  p.out = out; p.ldo = ldo; p.out_batch_stride = out_batch_stride; p.out_f32 = out_f32;
+  p.bias = bias; p.bias_row = bias_row;
+  p.residual = residual; p.ld_res = ld_res; p.res_batch_stride = res_batch_stride;
+  p.act = act; p.alpha = alpha;
+  p.out_mul = 1;
+
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch};
+    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(batch > 1 ? a_batch_stride : (long long)M * lda) * 2};
+    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    int r = encode_tmap(&ta, A, 3, dims, str, box, nullptr);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)(p.b_batched ? batch : 1)};
+    uint64_t str[2] = {(uint64_t)ldw * 2, (uint64_t)(p.b_batched ? w_batch_stride : (long long)N * ldw) * 2};
+    uint32_t box[3] = {kBlockK, (uint32_t)bn, 1};
+    int r = encode_tmap(&tb, W, 3, dims, str, box, nullptr);
+    if (r) return r;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return out_f32 ? launch_bn<float>(bn, ta, ta, tb, p, st) : launch_bn<__half>(bn, ta, ta, tb, p, st);
+}
+
+// Choose the (bw, bh) output-pixel patch of an M tile: bw*bh <= 128, maximise useful rows.
+static void pick_patch(int Ho, int Wo, int stride, int* bw_out, int* bh_out) {
+  double best = -1;
+  int bbw = 1, bbh = 1;
+  for (int bw = 1; bw <= 128 && bw <= Wo; ++bw) {
+    if (bw * stride > 256) break;
+    int bh = 128 / bw;
+    if (bh > Ho) bh = Ho;
+    if (bh * stride > 256) bh = 256 / stride;
+    if (bh < 1) continue;
+    long long tw = (Wo + bw - 1) / bw, th = (Ho + bh - 1) / bh;
+    double eff = (double)Ho * Wo / (double)(tw * th * 128);
+    // prefer wider rows on ties (longer contiguous TMA rows / stores)
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > bbw)) {
+      best = eff; bbw = bw; bbh = bh;
+    }
+  }
+  *bw_out = bbw; *bh_out = bbh;
+}
+
+extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, const void* X2, int C2,
+                                const void* Wp, int Cout, int num_taps, const int* tap_dy,
+                                const int* tap_dx, int stride, int Ho, int Wo, int out_mul, int out_oy,
+                                int out_ox, const float* bias, const float* rowvec,
+                                long long ld_rowvec, const void* residual, void* out, int out_f32,
+                                int out_nchw, int act, void* stream) {
+  B200_CHECK_ARG(X && Wp && out, "b200_conv2d_nhwc: null pointer");
+  B200_CHECK_ARG(Cin % 64 == 0, "b200_conv2d_nhwc: Cin=%d must be a multiple of 64 (use im2col path)", Cin);
+  B200_CHECK_ARG(C2 % 64 == 0, "b200_conv2d_nhwc: C2=%d must be a multiple of 64", C2);
+  B200_CHECK_ARG(num_taps >= 1 && num_taps <= kMaxTaps, "b200_conv2d_nhwc: num_taps=%d", num_taps);
+  B200_CHECK_ARG(stride >= 1 && stride <= 2 && out_mul >= 1, "b200_conv2d_nhwc: stride=%d out_mul=%d", stride, out_mul);
+  B200_CHECK_ARG(NB > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && Cout > 0, "b200_conv2d_nhwc: bad shape");
+  B200_CHECK_ARG(((uintptr_t)X & 15) == 0 && ((uintptr_t)Wp & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                 "b200_conv2d_nhwc: pointers must be 16-byte aligned");
+  B200_CHECK_ARG(act != ACT_GEGLU, "b200_conv2d_nhwc: GEGLU epilogue is linear-only");
+  B200_CHECK_ARG(!out_nchw || !residual, "b200_conv2d_nhwc: out_nchw excludes residual");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.conv = 1;
+  p.N = Cout;
+  p.batch = 1;
+  p.Ho = Ho; p.Wo = Wo;
+  pick_patch(Ho, Wo, stride, &p.bw, &p.bh);
+  p.tiles_w = (Wo + p.bw - 1) / p.bw;
+  p.tiles_h = (Ho + p.bh - 1) / p.bh;
+  p.m_tiles = NB * p.tiles_w * p.tiles_h;
+  p.M = NB * Ho * Wo;
+  p.cin_blocks = Cin / 64;
+  p.num_taps = num_taps;
+  p.in_stride = stride;
+  for (int i = 0; i < num_taps; ++i) { p.tap_dy[i] = tap_dy[i]; p.tap_dx[i] = tap_dx[i]; }
+  p.k2_blocks = X2 ? C2 / 64 : 0;
+  p.num_k_blocks = num_taps * p.cin_blocks + p.k2_blocks;
+  p.out_mul = out_mul; p.out_oy = out_oy; p.out_ox = out_ox;
+  p.OH = Ho * out_mul; p.OW = Wo * out_mul;
+  int bn = pick_block_n(Cout, p.m_tiles, g_force_bn);
+  p.n_tiles = (Cout + bn - 1) / bn;
+  p.out = out; p.ldo = Cout; p.out_f32 = out_f32; p.out_nchw = out_nchw;
+  p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec;
+  p.residual = residual; p.ld_res = Cout;
+  p.act = act; p.alpha = 1.0f;
+
+  CUtensorMap ta, ta2, tb;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {kBlockK, (uint32_t)(p.bw * stride), (uint32_t)(p.bh * stride), 1};
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int r = encode_tmap(&ta, X, 4, dims, str, box, es);
+    if (r) return r;
+  }
+  ta2 = ta;
+  if (X2) {
+    uint64_t dims[4] = {(uint64_t)C2, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)C2 * 2, (uint64_t)Wo * C2 * 2, (uint64_t)Ho * Wo * C2 * 2};
+    uint32_t box[4] = {kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    int r = encode_tmap(&ta2, X2, 4, dims, str, box, nullptr);
+    if (r) return r;
+  }
+  {
+    const long long Kt = (long long)num_taps * Cin + (X2 ? C2 : 0);
+    uint64_t dims[3] = {(uint64_t)Kt, (uint64_t)Cout, 1};
+    uint64_t str[2] = {(uint64_t)Kt * 2, (uint64_t)Kt * Cout * 2};
+    uint32_t box[3] = {kBlockK, (uint32_t)bn, 1};
+    int r = encode_tmap(&tb, Wp, 3, dims, str, box, nullptr);
+    if (r) return r;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return out_f32 ? launch_bn<float>(bn, ta, ta2, tb, p, st) : launch_bn<__half>(bn, ta, ta2, tb, p, st);
+}

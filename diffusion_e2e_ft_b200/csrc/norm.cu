@@ -1,0 +1,333 @@
+// HBM-bound normalisation kernels: GroupNorm (two-pass, NHWC, fused concat + SiLU), LayerNorm,
+// row softmax.  16-byte vectorised coalesced loads, warp-shuffle reductions, fp32 statistics.
+#include "common.cuh"
+#include "../../include/b200_e2eft.h"
+
+namespace b200 {
+
+__device__ __forceinline__ void load8(const __half* p, float* v) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8h(__half* p, const float* v) {
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------ GroupNorm stats
+// grid (chunks, NB); block T = V * rpb where V = C/8 vectors per pixel (each thread owns one fixed
+// 8-channel vector column and strides over pixels).  Per-channel partial sums -> smem -> per-group
+// -> double atomics into sums[n][g][2].
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ x1, int C1, const T* __restrict__ x2, int C2,
+                                int HW, int groups, int pix_per_cta, double* __restrict__ sums) {
+  extern __shared__ float sm[];   // [2][C]
+  const int C = C1 + C2;
+  const int V = C / 8;
+  const int n = blockIdx.y;
+  const int rpb = blockDim.x / V;
+  const int v = threadIdx.x % V;
+  const int r = threadIdx.x / V;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  const int c0 = v * 8;
+  const bool second = c0 >= C1;
+  const T* base = second ? x2 + (long long)n * HW * C2 + (c0 - C1) : x1 + (long long)n * HW * C1 + c0;
+  const int ld = second ? C2 : C1;
+  if (r < rpb) {
+    for (int p = p0 + r; p < p1; p += rpb) {
+      float f[8];
+      load8(base + (long long)p * ld, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] += f[e] * f[e]; }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sm[c0 + e], s[e]);
+      atomicAdd(&sm[C + c0 + e], q[e]);
+    }
+  }
+  __syncthreads();
+  const int cg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) { a += sm[c]; b += sm[C + c]; }
+    atomicAdd(&sums[((long long)n * groups + g) * 2 + 0], (double)a);
+    atomicAdd(&sums[((long long)n * groups + g) * 2 + 1], (double)b);
+  }
+}
+
+// ------------------------------------------------------------------------------ GroupNorm apply
+// grid (chunks, NB).  Per-(n,c) scale/shift precomputed into smem, then a pure streaming pass.
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ x1, int C1, const T* __restrict__ x2, int C2,
+                                int HW, int groups, int pix_per_cta, const double* __restrict__ sums,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float eps, int silu, __half* __restrict__ y, __half* __restrict__ raw) {
+  extern __shared__ float sm[];   // scale[C], shift[C]
+  const int C = C1 + C2;
+  const int V = C / 8;
+  const int n = blockIdx.y;
+  const int cg = C / groups;
+  const double cnt = (double)HW * cg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cg;
+    const double su = sums[((long long)n * groups + g) * 2 + 0];
+    const double sq = sums[((long long)n * groups + g) * 2 + 1];
+    const double mean = su / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float a = rstd * gamma[c];
+    sm[c] = a;
+    sm[C + c] = beta[c] - (float)mean * a;
+  }
+  __syncthreads();
+  const int rpb = blockDim.x / V;
+  const int v = threadIdx.x % V;
+  const int r = threadIdx.x / V;
+  if (r >= rpb) return;
+  const int c0 = v * 8;
+  const bool second = c0 >= C1;
+  const T* base = second ? x2 + (long long)n * HW * C2 + (c0 - C1) : x1 + (long long)n * HW * C1 + c0;
+  const int ld = second ? C2 : C1;
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = sm[c0 + e]; b[e] = sm[C + c0 + e]; }
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  __half* yb = y + (long long)n * HW * C + c0;
+  __half* rb = raw ? raw + (long long)n * HW * C + c0 : nullptr;
+  for (int p = p0 + r; p < p1; p += rpb) {
+    float f[8], o[8];
+    load8(base + (long long)p * ld, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = f[e] * a[e] + b[e];
+      o[e] = silu ? t / (1.0f + __expf(-t)) : t;
+    }
+    store8h(yb + (long long)p * C, o);
+    if (rb) store8h(rb + (long long)p * C, f);
+  }
+}
+
+static int gn_block(int C) {
+  const int V = C / 8;
+  if (V > 1024) return -1;
+  int rpb = 256 / V;
+  if (rpb < 1) rpb = 1;
+  return V * rpb;
+}
+
+// ------------------------------------------------------------------------------ LayerNorm
+// one warp per row; C <= 2048, C % 8 == 0.  Two-pass in registers (exact mean, then variance).
+template <typename T>
+__global__ void layer_norm_kernel(const T* __restrict__ x, long long rows, int C,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  float eps, __half* __restrict__ y) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int V = C / 8;
+  constexpr int kMaxV = 8;   // per-lane vectors: C <= 32*8*8 = 2048
+  float f[kMaxV][8];
+  float s = 0.f;
+  const T* xr = x + row * C;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      load8(xr + v * 8, f[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[i][e];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  __half* yr = y + row * C;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      float g[8], b[8], o[8];
+      load8(gamma + v * 8, g);
+      load8(beta + v * 8, b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (f[i][e] - mean) * rstd * g[e] + b[e];
+      store8h(yr + v * 8, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ row softmax
+// one CTA (256 threads) per row: fp32 logits -> fp16 probabilities; three streaming passes
+// (row re-reads hit L2: a 9216-float row is 36 KB).
+__global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, __half* __restrict__ P,
+                                    long long ldp, int cols, float scale) {
+  __shared__ float red[32];
+  const float* s = S + (long long)blockIdx.x * lds;
+  __half* p = P + (long long)blockIdx.x * ldp;
+  const int tid = threadIdx.x, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(s + c);
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  m = warp_max(m);
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  const float sl2 = scale * 1.4426950408889634f;
+  const float ms = m * sl2;
+  float sum = 0.f;
+  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(s + c);
+    sum += exp2f(v.x * sl2 - ms) + exp2f(v.y * sl2 - ms) + exp2f(v.z * sl2 - ms) + exp2f(v.w * sl2 - ms);
+  }
+  sum = warp_sum(sum);
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(s + c);
+    __half2 a = __floats2half2_rn(exp2f(v.x * sl2 - ms) * inv, exp2f(v.y * sl2 - ms) * inv);
+    __half2 b = __floats2half2_rn(exp2f(v.z * sl2 - ms) * inv, exp2f(v.w * sl2 - ms) * inv);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p + c) = u;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static int gn_common_check(const char* fn, const void* x1, int C1, const void* x2, int C2, int NB,
+                           int HW, int groups) {
+  const int C = C1 + C2;
+  B200_CHECK_ARG(x1 && C1 > 0 && NB > 0 && HW > 0, "%s: bad arguments", fn);
+  B200_CHECK_ARG((C2 == 0) == (x2 == nullptr), "%s: x2/C2 mismatch", fn);
+  B200_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0, "%s: channel counts must be multiples of 8 (C1=%d C2=%d)", fn, C1, C2);
+  B200_CHECK_ARG(groups > 0 && C % groups == 0, "%s: C=%d not divisible by groups=%d", fn, C, groups);
+  B200_CHECK_ARG(gn_block(C) > 0 && gn_block(C) <= 1024, "%s: C=%d unsupported", fn, C);
+  return 0;
+}
+
+static int gn_chunks(int NB, int HW, int rows_per_pass) {
+  // ~4 CTAs per SM across the batch, at least rows_per_pass pixels per CTA
+  int target = (sm_count() * 4 + NB - 1) / NB;
+  int ppc = (HW + target - 1) / target;
+  if (ppc < rows_per_pass * 4) ppc = rows_per_pass * 4;
+  return ppc;
+}
+
+extern "C" int b200_group_norm_stats(const void* x1, int C1, const void* x2, int C2, int in_f32, int NB,
+                                     int HW, int groups, double* sums, void* stream) {
+  int r = gn_common_check("b200_group_norm_stats", x1, C1, x2, C2, NB, HW, groups);
+  if (r) return r;
+  B200_CHECK_ARG(sums, "b200_group_norm_stats: null sums");
+  const int C = C1 + C2;
+  const int T = gn_block(C);
+  const int ppc = gn_chunks(NB, HW, T / (C / 8));
+  dim3 grid((HW + ppc - 1) / ppc, NB);
+  const size_t smem = 2 * C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_f32)
+    gn_stats_kernel<float><<<grid, T, smem, st>>>((const float*)x1, C1, (const float*)x2, C2, HW, groups, ppc, sums);
+  else
+    gn_stats_kernel<__half><<<grid, T, smem, st>>>((const __half*)x1, C1, (const __half*)x2, C2, HW, groups, ppc, sums);
+  B200_CHECK_LAUNCH("gn_stats_kernel");
+  return 0;
+}
+
+extern "C" int b200_group_norm_apply(const void* x1, int C1, const void* x2, int C2, int in_f32, int NB,
+                                     int HW, int groups, const double* sums, const float* gamma,
+                                     const float* beta, float eps, int silu, void* y, void* raw_copy,
+                                     void* stream) {
+  int r = gn_common_check("b200_group_norm_apply", x1, C1, x2, C2, NB, HW, groups);
+  if (r) return r;
+  B200_CHECK_ARG(sums && gamma && beta && y, "b200_group_norm_apply: null pointer");
+  const int C = C1 + C2;
+  const int T = gn_block(C);
+  const int ppc = gn_chunks(NB, HW, T / (C / 8));
+  dim3 grid((HW + ppc - 1) / ppc, NB);
+  const size_t smem = 2 * C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_f32)
+    gn_apply_kernel<float><<<grid, T, smem, st>>>((const float*)x1, C1, (const float*)x2, C2, HW, groups, ppc, sums,
+                                                  gamma, beta, eps, silu, (__half*)y, (__half*)raw_copy);
+  else
+    gn_apply_kernel<__half><<<grid, T, smem, st>>>((const __half*)x1, C1, (const __half*)x2, C2, HW, groups, ppc, sums,
+                                                   gamma, beta, eps, silu, (__half*)y, (__half*)raw_copy);
+  B200_CHECK_LAUNCH("gn_apply_kernel");
+  return 0;
+}
+
+extern "C" int b200_layer_norm(const void* x, int in_f32, long long rows, int C, const float* gamma,
+                               const float* beta, float eps, void* y, void* stream) {
+  B200_CHECK_ARG(x && y && gamma && beta && rows > 0, "b200_layer_norm: bad arguments");
+  B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "b200_layer_norm: C=%d must be a multiple of 8 and <= 2048", C);
+  const int wpb = 8;
+  const long long grid = (rows + wpb - 1) / wpb;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_f32)
+    layer_norm_kernel<float><<<(unsigned)grid, wpb * 32, 0, st>>>((const float*)x, rows, C, gamma, beta, eps, (__half*)y);
+  else
+    layer_norm_kernel<__half><<<(unsigned)grid, wpb * 32, 0, st>>>((const __half*)x, rows, C, gamma, beta, eps, (__half*)y);
+  B200_CHECK_LAUNCH("layer_norm_kernel");
+  return 0;
+}
+
+extern "C" int b200_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows,
+                                 int cols, float scale, void* stream) {
+  B200_CHECK_ARG(S && P && rows > 0 && cols > 0, "b200_softmax_rows: bad arguments");
+  B200_CHECK_ARG(cols % 4 == 0 && lds % 4 == 0 && ldp % 4 == 0, "b200_softmax_rows: cols/ld must be multiples of 4");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(S, lds, (__half*)P, ldp, cols, scale);
+  B200_CHECK_LAUNCH("softmax_rows_kernel");
+  return 0;
+}

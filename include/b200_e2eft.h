@@ -1,0 +1,142 @@
+/* b200_e2eft.h — C ABI of the B200-native single-step denoising engine (libb200_e2eft.so).
+ *
+ * Drop-in boundary for the hot path named by BASELINE.json `north_star`:
+ *   VAE.encode -> UNet2DConditionModel forward (t=999) -> x0 -> VAE.decode.
+ * The reference (VisualComputingInstitute/diffusion-e2e-ft) is pure Python and has no FFI of its
+ * own; every entry point below replaces the third-party library kernel (cuDNN / cuBLAS / xformers /
+ * ATen) behind one leaf operator of the reference's model graph.  The citation after each
+ * prototype is the reference call site (relative to /root/reference) the function serves.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are CUDA device pointers owned by the caller
+ *     (PyTorch allocates inputs, outputs and workspaces); the library never allocates or syncs;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 = ok; <0 = invalid argument (nothing launched); >0 = cudaError_t of the launch;
+ *     b200_last_error_string() describes the last failure on the calling thread;
+ *   - activations are NHWC ("channels last") fp16 operands; the residual stream may be fp16 or fp32
+ *     (`*_f32` flags); accumulation, normalisation statistics and softmax are always fp32;
+ *   - there is no CPU fallback: without an sm_100a device every launch returns an error.
+ */
+#ifndef B200_E2EFT_H_
+#define B200_E2EFT_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* b200_last_error_string(void);
+int b200_abi_version(void);
+
+/* epilogue activations */
+#define B200_ACT_NONE 0
+#define B200_ACT_SILU 1
+#define B200_ACT_GEGLU 2 /* W rows pre-interleaved per tile: [value half | gate half] */
+
+/* out[b][m][n] = act( alpha * sum_k A[b][m][k] * W[(b)][n][k] + bias + residual[b][m][n] )
+ * tcgen05 GEMM, fp16 operands (K contiguous), fp32 accumulate in TMEM.
+ * Replaces: nn.Linear of proj_in/proj_out (GeoWizard/geowizard/models/transformer_2d.py:152-155,
+ * 214-217), to_q/to_k/to_v/to_out (attention.py:470-478,501), GEGLU proj + FF out
+ * (attention.py:755,765), TimestepEmbedding / time_emb_proj / class_embedding
+ * (unet_2d_condition.py:974-1000); batched form = QK^T and PV of the VAE mid attention
+ * (unet_2d_blocks.py:589-601). */
+int b200_linear(const void* A, long long lda, long long a_batch_stride,
+                const void* W, long long ldw, long long w_batch_stride /* 0 = shared */,
+                int M, int N, int K, int batch,
+                const float* bias, int bias_row,
+                const void* residual, long long ld_res, long long res_batch_stride,
+                void* out, long long ldo, long long out_batch_stride, int out_f32,
+                int act, float alpha, void* stream);
+
+/* Implicit-GEMM convolution on NHWC fp16 input, weights packed [Cout][tap][Cin] (+[C2] shortcut
+ * columns), tcgen05 + TMA, no im2col buffer.  Tap t reads input pixel
+ * (ho*stride + tap_dy[t], wo*stride + tap_dx[t]); out-of-range pixels read as zero (padding).
+ * Output pixel (ho,wo) is written at (ho*out_mul+out_oy, wo*out_mul+out_ox) of an
+ * (Ho*out_mul x Wo*out_mul) NHWC (or NCHW when out_nchw) tensor.
+ *   out = act( conv(X) + conv1x1(X2) + bias[c] + rowvec[img][c] + residual )
+ * Replaces: ResnetBlock2D.conv1/conv2/conv_shortcut (instantiated at
+ * GeoWizard/geowizard/models/unet_2d_blocks.py:1064-1076,1211-1223,2242-2254,2400-2412,667-679),
+ * Downsample2D.conv (:1107-1113,1228-1234, VAE :1315-1321), Upsample2D.conv (:2285,2417),
+ * conv_out (unet_2d_condition.py:617-619) and the VAE encoder/decoder convs
+ * (Marigold/marigold/marigold_pipeline.py:493,516). */
+int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin,
+                     const void* X2, int C2,
+                     const void* Wp, int Cout, int num_taps, const int* tap_dy, const int* tap_dx,
+                     int stride, int Ho, int Wo, int out_mul, int out_oy, int out_ox,
+                     const float* bias, const float* rowvec, long long ld_rowvec,
+                     const void* residual, void* out, int out_f32, int out_nchw, int act,
+                     void* stream);
+
+/* Patch matrix for the small-Cin input convolutions (conv_in: 8->320, 3->128, 4->512):
+ * out[pixel][tap*Cin + c] fp16, row length Kpad (zero padded).  `x` is NCHW (x_f32 ? fp32 : fp16).
+ * Serves unet_2d_condition.py:294-296,1084 and the VAE conv_in. */
+int b200_im2col3x3_nchw(const void* x, int x_f32, int NB, int C, int H, int W, void* out,
+                        int Kpad, void* stream);
+
+/* GroupNorm statistics over NHWC input that is the channel-concatenation of up to two tensors
+ * (skip-connection concat, unet_2d_blocks.py:2328,2456, is never materialised).
+ * sums[n][g][2] (double) must be zeroed by the caller. */
+int b200_group_norm_stats(const void* x1, int C1, const void* x2, int C2, int in_f32, int NB,
+                          int HW, int groups, double* sums, void* stream);
+/* y = [silu]( (x-mean)*rstd*gamma + beta ) as fp16 NHWC; optional raw fp16 copy of the
+ * (concatenated) input for the 1x1 shortcut operand.
+ * Replaces GroupNorm+SiLU of ResnetBlock2D norm1/norm2, conv_norm_out
+ * (unet_2d_condition.py:605-610,1209-1211) and Transformer2DModel.norm (transformer_2d.py:151,331). */
+int b200_group_norm_apply(const void* x1, int C1, const void* x2, int C2, int in_f32, int NB, int HW,
+                          int groups, const double* sums, const float* gamma, const float* beta,
+                          float eps, int silu, void* y, void* raw_copy, void* stream);
+
+/* LayerNorm over the last dim of [rows][C] (in_f32 ? fp32 : fp16) -> fp16.
+ * Replaces BasicTransformerBlock.norm1/2/3 (attention.py:205,237,264). */
+int b200_layer_norm(const void* x, int in_f32, long long rows, int C, const float* gamma,
+                    const float* beta, float eps, void* y, void* stream);
+
+/* Flash attention, head_dim 64, fp16 Q/K/V read in place from (possibly fused) projection
+ * buffers: element (b, l, h, d) of Q is q[b*q_bs + l*q_ls + h*64 + d] (same for K, V).
+ * `kv_segments` = 2 implements GeoWizard's joint self-attention: batch element b attends to the
+ * keys/values of b%(B/2) and b%(B/2)+B/2 concatenated (attention.py:482-491).
+ * out[b][l][h*64+d] fp16 with row stride o_ls.   softmax(QK^T*scale)V, fp32 softmax.
+ * Replaces xformers.ops.memory_efficient_attention (attention.py:497) / attn1, attn2
+ * (attention.py:338-343,375-380). */
+int b200_attention_d64(const void* q, long long q_bs, long long q_ls,
+                       const void* k, long long k_bs, long long k_ls,
+                       const void* v, long long v_bs, long long v_ls,
+                       void* out, long long o_bs, long long o_ls,
+                       int B, int heads, int Lq, int Lk, int kv_segments, float scale, void* stream);
+
+/* Row softmax: P[r][:] = softmax(scale * S[r][:]) fp32 -> fp16 (VAE mid-block attention, d=512). */
+int b200_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows,
+                      int cols, float scale, void* stream);
+
+/* Nearest-neighbour resize NHWC (in_f32 ? fp32 : fp16) -> fp16 (Upsample2D interpolate,
+ * exact 2x or explicit `size=`, unet_2d_condition.py:1185-1186). */
+int b200_upsample_nearest_nhwc(const void* x, int in_f32, int NB, int H, int W, int C, int OH,
+                               int OW, void* y, void* stream);
+
+/* Sinusoidal timestep embedding (flip_sin_to_cos, freq_shift 0) -> fp16 [B][dim].
+ * t is a device array of B floats.  unet_2d_condition.py:974. */
+int b200_timestep_embedding(const float* t, int B, int dim, void* out, void* stream);
+
+/* Small dense per-pixel channel mix on NCHW fp32 (Cin, Cout <= 8):
+ * out[n][co][p] = sum_ci Wm[co][ci] * (a1*in1[n][ci][p] + a2*in2[n][ci][p]) + bias[co].
+ * Serves quant_conv + latent scaling (marigold_pipeline.py:494-497) and
+ * pred_original_sample + /0.18215 + post_quant_conv (:457-465,513-515). */
+int b200_pointwise_nchw(const float* in1, float a1, const float* in2, float a2, int in_cstride,
+                        const float* Wm, const float* bias, int NB, int Cin, int Cout, long long HW,
+                        float* out, void* stream);
+
+/* Decode post-ops on NCHW fp32 [B][3][HW]: mode 0 = depth: (clip(mean_c, -1, 1)+1)/2 -> [B][1][HW];
+ * mode 1 = normals: x/(||x||_2+1e-5) * sign -> [B][3][HW].  marigold_pipeline.py:467-478. */
+int b200_decode_post(const float* x, int NB, long long HW, int mode, float sign, float* out,
+                     void* stream);
+
+/* fp32 <-> fp16 casts / layout helpers used at module boundaries. */
+int b200_cast_f32_to_f16(const float* x, void* y, long long n, void* stream);
+int b200_nhwc_to_nchw_f32(const void* x, int in_f32, int NB, int C, long long HW, float* y, void* stream);
+
+/* debugging: force a BLOCK_N (0 = automatic) */
+void b200_debug_force_block_n(int bn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_E2EFT_H_ */
