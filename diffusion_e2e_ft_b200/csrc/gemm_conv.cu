@@ -146,6 +146,11 @@ using namespace b200;
 extern "C" const char* b200_last_error_string(void) { return b200::last_error(); }
 extern "C" void b200_debug_force_block_n(int bn) { b200::g_force_bn = bn; }
 extern "C" int b200_abi_version(void) { return 1; }
+// Tile width used by the GEGLU epilogue for a packed width N (= 2 x output width); weights must be
+// packed per tile as [value half | gate half] with this width.
+extern "C" int b200_geglu_block_n(int N) {
+  return (N % 160 == 0) ? 160 : (N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 0)));
+}
 
 extern "C" int b200_linear(const void* A, long long lda, long long a_batch_stride, const void* W,
                            long long ldw, long long w_batch_stride, int M, int N, int K, int batch,
@@ -158,7 +163,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "b200_linear: lda/ldw must be multiples of 8 elements (16 B)");
   B200_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
                  "b200_linear: pointers must be 16-byte aligned");
-  B200_CHECK_ARG(ldo % 8 == 0 || N % 8 != 0, "b200_linear: ldo must be a multiple of 8");
+  B200_CHECK_ARG(act != ACT_GEGLU || ldo % 8 == 0, "b200_linear: GEGLU needs ldo %% 8 == 0");
   B200_CHECK_ARG(act != ACT_GEGLU || (N % 16 == 0 && bias), "b200_linear: GEGLU needs bias and N%%16==0");
   B200_CHECK_ARG(batch == 1 || (a_batch_stride % 8 == 0 && (w_batch_stride % 8 == 0)),
                  "b200_linear: batch strides must be multiples of 8 elements");
@@ -169,9 +174,10 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.num_k_blocks = (K + kBlockK - 1) / kBlockK;
   p.batch = batch;
   p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.a_batched = (a_batch_stride != 0 && batch > 1);
   p.b_batched = (w_batch_stride != 0 && batch > 1);
   int bn = pick_block_n(N, (long long)p.m_tiles * batch, g_force_bn);
-  if (act == ACT_GEGLU) bn = (N % 160 == 0 && g_force_bn == 0) ? 160 : (N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 0));
+  if (act == ACT_GEGLU) bn = b200_geglu_block_n(N);
   B200_CHECK_ARG(bn != 0, "b200_linear: GEGLU N=%d not tileable", N);
   p.n_tiles = (N + bn - 1) / bn;
   p.out = out; p.ldo = ldo; p.out_batch_stride = out_batch_stride; p.out_f32 = out_f32;
@@ -179,11 +185,13 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.residual = residual; p.ld_res = ld_res; p.res_batch_stride = res_batch_stride;
   p.act = act; p.alpha = alpha;
   p.out_mul = 1;
+  p.vec_ok = (ldo % 8 == 0) && (out_batch_stride % 8 == 0) &&
+             (!residual || (ld_res % 8 == 0 && res_batch_stride % 8 == 0 && ((uintptr_t)residual & 15) == 0));
 
   CUtensorMap ta, tb;
   {
-    uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch};
-    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(batch > 1 ? a_batch_stride : (long long)M * lda) * 2};
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(p.a_batched ? batch : 1)};
+    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(p.a_batched ? a_batch_stride : (long long)M * lda) * 2};
     uint32_t box[3] = {kBlockK, kBlockM, 1};
     int r = encode_tmap(&ta, A, 3, dims, str, box, nullptr);
     if (r) return r;
@@ -261,6 +269,7 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec;
   p.residual = residual; p.ld_res = Cout;
   p.act = act; p.alpha = 1.0f;
+  p.vec_ok = (Cout % 8 == 0) && (!residual || ((uintptr_t)residual & 15) == 0);
 
   CUtensorMap ta, ta2, tb;
   {

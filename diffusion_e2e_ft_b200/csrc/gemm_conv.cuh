@@ -32,7 +32,7 @@ enum EpiAct { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2 };
 struct GemmParams {
   int M, N, num_k_blocks;
   int batch, m_tiles, n_tiles;
-  int b_batched;               // W operand has a batch dimension (else shared across batch)
+  int a_batched, b_batched;    // operand has a batch dimension (else shared across the batch)
   // ---- conv geometry (conv != 0)
   int conv;
   int Ho, Wo;                  // conv-output grid the M tiles walk over
@@ -46,6 +46,7 @@ struct GemmParams {
   void* out;
   long long ldo, out_batch_stride;
   int out_f32;
+  int vec_ok;                  // 16-byte vector stores/loads are aligned (ldo, ld_res % 8 == 0)
   int out_nchw;                // conv only: write fp32/fp16 NCHW (small Cout) instead of NHWC
   const float* bias;           // [N] (or [M] when bias_row)
   int bias_row;
@@ -190,7 +191,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                           kEvictNormal);
             }
           } else {
-            tma_load_3d(&tmA, &full_bar[stage], sa, kb * kBlockK, m_blk * kBlockM, b, kEvictNormal);
+            tma_load_3d(&tmA, &full_bar[stage], sa, kb * kBlockK, m_blk * kBlockM, p.a_batched ? b : 0,
+                        kEvictNormal);
           }
           tma_load_3d(&tmB, &full_bar[stage], sb, kb * kBlockK, n_blk * BLOCK_N, p.b_batched ? b : 0,
                       kEvictLast);
@@ -343,7 +345,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (p.act == ACT_SILU) v = silu_f(v);
                     out[((long long)img * p.N + col + e) * plane + opix] = (OutT)v;
                   }
-                } else if (col + 8 <= p.N) {
+                } else if (p.vec_ok && col + 8 <= p.N) {
                   if (rrow_ptr) {
                     float rr[8];
                     load_chunk8<OutT>(rrow_ptr + col, rr);

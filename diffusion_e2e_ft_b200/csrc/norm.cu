@@ -201,7 +201,8 @@ __global__ void layer_norm_kernel(const T* __restrict__ x, long long rows, int C
 
 // ------------------------------------------------------------------------------ row softmax
 // one CTA (256 threads) per row: fp32 logits -> fp16 probabilities; three streaming passes
-// (row re-reads hit L2: a 9216-float row is 36 KB).
+// (row re-reads hit L2: a 9216-float row is 36 KB).  VEC = 4 when cols and strides are %4.
+template <int VEC>
 __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, __half* __restrict__ P,
                                     long long ldp, int cols, float scale) {
   __shared__ float red[32];
@@ -209,9 +210,13 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, 
   __half* p = P + (long long)blockIdx.x * ldp;
   const int tid = threadIdx.x, nw = blockDim.x >> 5;
   float m = -INFINITY;
-  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
-    float4 v = *reinterpret_cast<const float4*>(s + c);
-    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  for (int c = tid * VEC; c < cols; c += blockDim.x * VEC) {
+    if constexpr (VEC == 4) {
+      float4 v = *reinterpret_cast<const float4*>(s + c);
+      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    } else {
+      m = fmaxf(m, s[c]);
+    }
   }
   m = warp_max(m);
   if ((tid & 31) == 0) red[tid >> 5] = m;
@@ -222,9 +227,13 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, 
   const float sl2 = scale * 1.4426950408889634f;
   const float ms = m * sl2;
   float sum = 0.f;
-  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
-    float4 v = *reinterpret_cast<const float4*>(s + c);
-    sum += exp2f(v.x * sl2 - ms) + exp2f(v.y * sl2 - ms) + exp2f(v.z * sl2 - ms) + exp2f(v.w * sl2 - ms);
+  for (int c = tid * VEC; c < cols; c += blockDim.x * VEC) {
+    if constexpr (VEC == 4) {
+      float4 v = *reinterpret_cast<const float4*>(s + c);
+      sum += exp2f(v.x * sl2 - ms) + exp2f(v.y * sl2 - ms) + exp2f(v.z * sl2 - ms) + exp2f(v.w * sl2 - ms);
+    } else {
+      sum += exp2f(s[c] * sl2 - ms);
+    }
   }
   sum = warp_sum(sum);
   if ((tid & 31) == 0) red[tid >> 5] = sum;
@@ -232,14 +241,18 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, 
   sum = 0.f;
   for (int i = 0; i < nw; ++i) sum += red[i];
   const float inv = 1.0f / sum;
-  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
-    float4 v = *reinterpret_cast<const float4*>(s + c);
-    __half2 a = __floats2half2_rn(exp2f(v.x * sl2 - ms) * inv, exp2f(v.y * sl2 - ms) * inv);
-    __half2 b = __floats2half2_rn(exp2f(v.z * sl2 - ms) * inv, exp2f(v.w * sl2 - ms) * inv);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p + c) = u;
+  for (int c = tid * VEC; c < cols; c += blockDim.x * VEC) {
+    if constexpr (VEC == 4) {
+      float4 v = *reinterpret_cast<const float4*>(s + c);
+      __half2 a = __floats2half2_rn(exp2f(v.x * sl2 - ms) * inv, exp2f(v.y * sl2 - ms) * inv);
+      __half2 b = __floats2half2_rn(exp2f(v.z * sl2 - ms) * inv, exp2f(v.w * sl2 - ms) * inv);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(p + c) = u;
+    } else {
+      p[c] = __float2half_rn(exp2f(s[c] * sl2 - ms) * inv);
+    }
   }
 }
 
@@ -326,8 +339,11 @@ extern "C" int b200_layer_norm(const void* x, int in_f32, long long rows, int C,
 extern "C" int b200_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows,
                                  int cols, float scale, void* stream) {
   B200_CHECK_ARG(S && P && rows > 0 && cols > 0, "b200_softmax_rows: bad arguments");
-  B200_CHECK_ARG(cols % 4 == 0 && lds % 4 == 0 && ldp % 4 == 0, "b200_softmax_rows: cols/ld must be multiples of 4");
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(S, lds, (__half*)P, ldp, cols, scale);
+  const bool vec = cols % 4 == 0 && lds % 4 == 0 && ldp % 4 == 0 && ((uintptr_t)S & 15) == 0 && ((uintptr_t)P & 7) == 0;
+  if (vec)
+    softmax_rows_kernel<4><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(S, lds, (__half*)P, ldp, cols, scale);
+  else
+    softmax_rows_kernel<1><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(S, lds, (__half*)P, ldp, cols, scale);
   B200_CHECK_LAUNCH("softmax_rows_kernel");
   return 0;
 }

@@ -1,0 +1,284 @@
+"""Building blocks of the engine: diffusers-named parameter containers whose forward runs the
+sm_100a kernels of libb200_e2eft.so (via ops.py) on NHWC activations.
+
+Layout / precision contract inside the engine
+  * activations are NHWC; GEMM/conv operands are fp16; accumulation fp32;
+  * the residual stream (`sdt`) is fp32 (parity mode, default) or fp16 (fast mode);
+  * GroupNorm / LayerNorm statistics and softmax are fp32.
+
+Each block mirrors one diffusers/GeoWizard class (cited per class) and keeps its `state_dict`
+names, so reference checkpoints load unchanged.  Packed fp16 weights are
+derived lazily from the fp32 master parameters and re-derived whenever a parameter changes
+(`_version` / storage pointer), so optimizers and `load_state_dict` just work.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import F16, F32
+
+
+class ConfigDict(dict):
+    """dict with attribute access — the reference reads both `unet.config.x` and `unet.config['x']`
+    (training/train.py:299, training/util/unet_prep.py:20)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class Packed:
+    """Cache of derived (packed fp16 / fp32-contiguous) tensors keyed on parameter identity+version."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, params, build):
+        key = tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in params)
+        if key != self._key:
+            with torch.no_grad():
+                self._val = build()
+            self._key = key
+        return self._val
+
+
+def _f32(p):
+    return p.detach().to(F32).contiguous()
+
+
+def _f16(p):
+    return p.detach().to(F16).contiguous()
+
+
+# ------------------------------------------------------------------------------------ resnet
+class ResnetBlock2D(nn.Module):
+    """diffusers ResnetBlock2D: GN+SiLU -> conv3x3 (+temb) -> GN+SiLU ->
+    conv3x3 (+1x1 shortcut fused as extra K columns) + residual.  Instantiated by the reference at
+    GeoWizard/geowizard/models/unet_2d_blocks.py:1064-1076, 2242-2254, 667-679."""
+
+    def __init__(self, cin, cout, temb_channels=1280, groups=32, eps=1e-5):
+        super().__init__()
+        self.cin, self.cout, self.groups, self.eps = cin, cout, groups, eps
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, cout) if temb_channels is not None else None
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+        self._pk = Packed()
+
+    def _packed(self):
+        ps = [p for p in self.parameters()]
+
+        def build():
+            d = dict(g1=_f32(self.norm1.weight), b1=_f32(self.norm1.bias),
+                     g2=_f32(self.norm2.weight), b2=_f32(self.norm2.bias),
+                     w1=ops.pack_conv(self.conv1.weight), c1b=_f32(self.conv1.bias))
+            if self.conv_shortcut is not None:
+                d["w2"] = ops.pack_conv(self.conv2.weight, self.conv_shortcut.weight)
+                d["c2b"] = _f32(self.conv2.bias + self.conv_shortcut.bias)
+            else:
+                d["w2"] = ops.pack_conv(self.conv2.weight)
+                d["c2b"] = _f32(self.conv2.bias)
+            return d
+        return self._pk.get(ps, build)
+
+    def run(self, x, temb=None, skip=None, sdt=F32):
+        """x (and optional skip, channel-concatenated after x): stream NHWC; temb: fp32 [B,cout] view."""
+        pk = self._packed()
+        if self.conv_shortcut is not None:
+            a1, raw = ops.group_norm(x, pk["g1"], pk["b1"], self.eps, self.groups, True, x2=skip, want_raw=True)
+        else:
+            assert skip is None
+            a1, raw = ops.group_norm(x, pk["g1"], pk["b1"], self.eps, self.groups, True), None
+        h = ops.conv2d(a1, pk["w1"], self.cout, bias=pk["c1b"], rowvec=temb)
+        a2 = ops.group_norm(h, pk["g2"], pk["b2"], self.eps, self.groups, True)
+        if raw is not None:
+            return ops.conv2d(a2, pk["w2"], self.cout, bias=pk["c2b"], x2=raw, out_dtype=sdt)
+        return ops.conv2d(a2, pk["w2"], self.cout, bias=pk["c2b"], residual=x, out_dtype=sdt)
+
+
+class Downsample2D(nn.Module):
+    """diffusers Downsample2D (App. A.4): stride-2 conv, pad 1 (UNet) or (0,1,0,1) (VAE encoder)."""
+
+    def __init__(self, ch, padding=1):
+        super().__init__()
+        self.ch, self.padding = ch, padding
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=padding)
+        self._pk = Packed()
+
+    def run(self, x, sdt=F32):
+        pk = self._pk.get(list(self.parameters()),
+                          lambda: dict(w=ops.pack_conv(self.conv.weight), b=_f32(self.conv.bias)))
+        NB, H, W, C = x.shape
+        if self.padding == 1:
+            taps, Ho, Wo = ops.TAPS3, (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        else:
+            taps, Ho, Wo = ops.TAPS3_PAD0, (H - 2) // 2 + 1, (W - 2) // 2 + 1
+        x16 = x if x.dtype == F16 else ops.cast_f16(x)
+        return ops.conv2d(x16, pk["w"], C, bias=pk["b"], taps=taps, stride=2, out_hw=(Ho, Wo), out_dtype=sdt)
+
+
+class Upsample2D(nn.Module):
+    """diffusers Upsample2D: nearest x2 (or explicit size, unet_2d_condition.py:1185-1186) + conv3x3."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.ch = ch
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+        self._pk = Packed()
+
+    def run(self, x, out_hw=None, sdt=F32):
+        pk = self._pk.get(list(self.parameters()),
+                          lambda: dict(w=ops.pack_conv(self.conv.weight), b=_f32(self.conv.bias)))
+        NB, H, W, C = x.shape
+        up = ops.upsample_nearest(x, out_hw or (2 * H, 2 * W))
+        return ops.conv2d(up, pk["w"], C, bias=pk["b"], out_dtype=sdt)
+
+
+# ------------------------------------------------------------------------------------ attention
+class Attention(nn.Module):
+    """Parameter container for diffusers `Attention` (to_q/to_k/to_v/to_out.0); the math runs in
+    BasicTransformerBlock.run so projections can be fused (QKV in one GEMM)."""
+
+    def __init__(self, dim, cross_dim=None, bias=False):
+        super().__init__()
+        self.to_q = nn.Linear(dim, dim, bias=bias)
+        self.to_k = nn.Linear(cross_dim or dim, dim, bias=bias)
+        self.to_v = nn.Linear(cross_dim or dim, dim, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+
+class BasicTransformerBlock(nn.Module):
+    """GeoWizard/geowizard/models/attention.py:292-413: LN -> self-attn -> LN -> cross-attn -> LN ->
+    GEGLU FF, each with residual.  `joint=True` = XFormersJointAttnProcessor (attention.py:430-513)."""
+
+    def __init__(self, dim, heads, cross_dim, joint=False):
+        super().__init__()
+        assert dim == heads * 64, "engine attention kernel is specialised for head_dim 64"
+        self.dim, self.heads, self.joint = dim, heads, joint
+        self.norm1 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn1 = Attention(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn2 = Attention(dim, cross_dim=cross_dim)
+        self.norm3 = nn.LayerNorm(dim, eps=1e-5)
+        self.ff = FeedForward(dim)
+        self._pk = Packed()
+
+    def _packed(self):
+        def build():
+            a1, a2 = self.attn1, self.attn2
+            wg, bg = ops.pack_geglu(self.ff.net[0].proj.weight, self.ff.net[0].proj.bias)
+            return dict(
+                ln=[(_f32(n.weight), _f32(n.bias)) for n in (self.norm1, self.norm2, self.norm3)],
+                wqkv=_f16(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0)),
+                wo1=_f16(a1.to_out[0].weight), bo1=_f32(a1.to_out[0].bias),
+                wq2=_f16(a2.to_q.weight), wkv2=_f16(torch.cat([a2.to_k.weight, a2.to_v.weight], 0)),
+                wo2=_f16(a2.to_out[0].weight), bo2=_f32(a2.to_out[0].bias),
+                wg=wg, bg=bg, wf=_f16(self.ff.net[2].weight), bf=_f32(self.ff.net[2].bias))
+        return self._pk.get(list(self.parameters()), build)
+
+    def run(self, h, B, L, ctx16, sdt=F32):
+        """h: stream [B*L, C]; ctx16: fp16 [B, S, Dctx]."""
+        pk = self._packed()
+        C, heads = self.dim, self.heads
+        scale = 64 ** -0.5
+        n1 = ops.layer_norm(h, *pk["ln"][0])
+        qkv = ops.linear(n1, pk["wqkv"]).view(B, L, 3 * C)
+        o = ops.attention_d64(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, scale,
+                              kv_segments=2 if self.joint else 1)
+        h = ops.linear(o.view(B * L, C), pk["wo1"], pk["bo1"], residual=h, out_dtype=sdt)
+        n2 = ops.layer_norm(h, *pk["ln"][1])
+        q2 = ops.linear(n2, pk["wq2"]).view(B, L, C)
+        S = ctx16.shape[1]
+        kv = ops.linear(ctx16.reshape(B * S, -1), pk["wkv2"]).view(B, S, 2 * C)
+        o2 = ops.attention_d64(q2, kv[..., :C], kv[..., C:], heads, scale)
+        h = ops.linear(o2.view(B * L, C), pk["wo2"], pk["bo2"], residual=h, out_dtype=sdt)
+        n3 = ops.layer_norm(h, *pk["ln"][2])
+        g = ops.linear(n3, pk["wg"], pk["bg"], act=ops.ACT_GEGLU)
+        return ops.linear(g, pk["wf"], pk["bf"], residual=h, out_dtype=sdt)
+
+
+class Transformer2DModel(nn.Module):
+    """GeoWizard/geowizard/models/transformer_2d.py:327-347,407-423 (continuous input, linear
+    projections): GN -> proj_in -> blocks -> proj_out -> + residual."""
+
+    def __init__(self, dim, heads, cross_dim, groups=32, joint=False):
+        super().__init__()
+        self.dim, self.groups = dim, groups
+        self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
+        self.proj_in = nn.Linear(dim, dim)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(dim, heads, cross_dim, joint)])
+        self.proj_out = nn.Linear(dim, dim)
+        self._pk = Packed()
+
+    def run(self, x, ctx16, sdt=F32):
+        own = [self.norm.weight, self.norm.bias, self.proj_in.weight, self.proj_in.bias,
+               self.proj_out.weight, self.proj_out.bias]
+        pk = self._pk.get(own, lambda: dict(g=_f32(self.norm.weight), b=_f32(self.norm.bias),
+                                            wi=_f16(self.proj_in.weight), bi=_f32(self.proj_in.bias),
+                                            wo=_f16(self.proj_out.weight), bo=_f32(self.proj_out.bias)))
+        B, H, W, C = x.shape
+        L = H * W
+        hn = ops.group_norm(x, pk["g"], pk["b"], 1e-6, self.groups, False)
+        h = ops.linear(hn.view(B * L, C), pk["wi"], pk["bi"], out_dtype=sdt)
+        for blk in self.transformer_blocks:
+            h = blk.run(h, B, L, ctx16, sdt)
+        h16 = h if h.dtype == F16 else ops.cast_f16(h)
+        out = ops.linear(h16, pk["wo"], pk["bo"], residual=x.view(B * L, C), out_dtype=sdt)
+        return out.view(B, H, W, C)
+
+
+# ------------------------------------------------------------------------------------ small-Cin conv
+class ConvInSmall:
+    """Helper for conv_in layers with Cin in {3,4,8}: im2col kernel + GEMM straight from NCHW."""
+
+    def __init__(self, conv: nn.Conv2d):
+        self.conv = conv
+        self._pk = Packed()
+
+    def run(self, x_nchw, sdt=F32):
+        conv = self.conv
+        cin, cout = conv.weight.shape[1], conv.weight.shape[0]
+        kpad = (9 * cin + 7) // 8 * 8
+        pk = self._pk.get([conv.weight, conv.bias],
+                          lambda: dict(w=ops.pack_conv_small_cin(conv.weight, kpad), b=_f32(conv.bias)))
+        NB, _, H, W = x_nchw.shape
+        patches = ops.im2col3x3(x_nchw.contiguous(), kpad)
+        return ops.linear(patches, pk["w"], pk["b"], out_dtype=sdt).view(NB, H, W, cout)
+
+
+class ConvOutSmall:
+    """GroupNorm+SiLU -> conv3x3 with tiny Cout (4 / 3 / 8), written as NCHW fp32."""
+
+    def __init__(self, norm: nn.GroupNorm, conv: nn.Conv2d):
+        self.norm, self.conv = norm, conv
+        self._pk = Packed()
+
+    def run(self, x):
+        norm, conv = self.norm, self.conv
+        pk = self._pk.get([norm.weight, norm.bias, conv.weight, conv.bias],
+                          lambda: dict(g=_f32(norm.weight), b=_f32(norm.bias),
+                                       w=ops.pack_conv(conv.weight), cb=_f32(conv.bias)))
+        a = ops.group_norm(x, pk["g"], pk["b"], norm.eps, norm.num_groups, True)
+        return ops.conv2d(a, pk["w"], conv.weight.shape[0], bias=pk["cb"], out_dtype=F32, out_nchw=True)

@@ -1,0 +1,267 @@
+"""Torch-tensor wrappers over the C ABI (PyTorch tensors in, PyTorch tensors out).
+
+PyTorch only owns memory and streams here: every arithmetic op is a kernel of libb200_e2eft.so
+launched on `torch.cuda.current_stream()`.  Nothing in this module computes with torch ops.
+"""
+import ctypes
+from ctypes import c_int, c_void_p
+
+import torch
+
+from . import lib as _lib
+
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+F16, F32 = torch.float16, torch.float32
+
+TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]        # pad=1
+TAPS3_PAD0 = [(ky, kx) for ky in range(3) for kx in range(3)]           # VAE downsample (0,1,0,1) pad
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("diffusion_e2e_ft_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------ weight packing
+def pack_conv(w, shortcut_w=None, taps=None):
+    """[Cout,Cin,kh,kw] -> fp16 [Cout, taps*Cin (+Cin2)], tap-major / channel-minor (K contiguous)."""
+    cout = w.shape[0]
+    wp = w.detach().permute(0, 2, 3, 1).reshape(cout, -1)
+    if shortcut_w is not None:
+        wp = torch.cat([wp, shortcut_w.detach().reshape(cout, -1)], dim=1)
+    return wp.to(F16).contiguous()
+
+
+def pack_conv_small_cin(w, kpad):
+    """conv_in weights for the im2col path: [Cout, 9*Cin] zero padded to kpad."""
+    cout = w.shape[0]
+    wp = w.detach().permute(0, 2, 3, 1).reshape(cout, -1)
+    out = torch.zeros(cout, kpad, dtype=F16, device=w.device)
+    out[:, :wp.shape[1]] = wp.to(F16)
+    return out
+
+
+def geglu_block_n(n):
+    bn = _lib.load().b200_geglu_block_n(int(n))
+    if bn == 0:
+        raise RuntimeError(f"GEGLU width {n} is not tileable")
+    return bn
+
+
+def pack_geglu(w, b):
+    """Interleave value/gate rows per output tile so the epilogue finds both halves in one tile."""
+    n = w.shape[0]
+    bn = geglu_block_n(n)
+    h = bn // 2
+    half = n // 2
+    idx = []
+    for t in range(n // bn):
+        idx += list(range(t * h, (t + 1) * h)) + list(range(half + t * h, half + (t + 1) * h))
+    idx = torch.tensor(idx, device=w.device)
+    return w.detach()[idx].to(F16).contiguous(), b.detach()[idx].to(F32).contiguous()
+
+
+# ------------------------------------------------------------------------------ GEMM
+def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE, alpha=1.0,
+           bias_row=False):
+    """a: [M,K] or [B,M,K] fp16 (last dim contiguous); w: [N,K] or [B,N,K] fp16."""
+    _need_cuda(a, w)
+    assert a.dtype == F16 and w.dtype == F16 and a.stride(-1) == 1 and w.stride(-1) == 1
+    batched = a.dim() == 3 or w.dim() == 3
+    B = (a.shape[0] if a.dim() == 3 else w.shape[0]) if batched else 1
+    M, K = a.shape[-2], a.shape[-1]
+    N = w.shape[-2]
+    assert w.shape[-1] == K
+    n_out = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        out = torch.empty((B, M, n_out) if batched else (M, n_out), dtype=out_dtype, device=a.device)
+    assert out.stride(-1) == 1
+    if residual is not None:
+        assert residual.dtype == out.dtype and residual.stride(-1) == 1
+    rc = _lib.load().b200_linear(
+        _p(a), a.stride(-2), a.stride(0) if a.dim() == 3 else 0,
+        _p(w), w.stride(-2), (w.stride(0) if w.dim() == 3 else 0),
+        M, N, K, B, _p(bias), int(bias_row),
+        _p(residual), residual.stride(-2) if residual is not None else 0,
+        (residual.stride(0) if (residual is not None and batched) else 0),
+        _p(out), out.stride(-2), out.stride(0) if batched else 0, int(out.dtype == F32),
+        act, float(alpha), _stream())
+    _lib.check(rc, "b200_linear")
+    return out
+
+
+# ------------------------------------------------------------------------------ conv
+def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, rowvec=None,
+           residual=None, out=None, out_dtype=F16, out_nchw=False, act=ACT_NONE,
+           out_mul=1, out_off=(0, 0)):
+    """x: NHWC fp16 [NB,H,W,Cin]; wp: packed fp16 [Cout, len(taps)*Cin (+C2)]."""
+    _need_cuda(x, wp)
+    assert x.dtype == F16 and x.is_contiguous() and wp.dtype == F16 and wp.is_contiguous()
+    NB, H, W, Cin = x.shape
+    Ho, Wo = out_hw if out_hw is not None else (H, W)
+    C2 = 0
+    if x2 is not None:
+        assert x2.dtype == F16 and x2.is_contiguous() and tuple(x2.shape[:3]) == (NB, Ho, Wo)
+        C2 = x2.shape[3]
+    assert wp.shape == (cout, len(taps) * Cin + C2), (wp.shape, cout, len(taps), Cin, C2)
+    if out is None:
+        shape = (NB, cout, Ho * out_mul, Wo * out_mul) if out_nchw else (NB, Ho * out_mul, Wo * out_mul, cout)
+        out = torch.empty(shape, dtype=out_dtype, device=x.device)
+    if residual is not None:
+        assert residual.dtype == out.dtype and residual.is_contiguous() and residual.shape == out.shape
+    dy = (c_int * len(taps))(*[t[0] for t in taps])
+    dx = (c_int * len(taps))(*[t[1] for t in taps])
+    rc = _lib.load().b200_conv2d_nhwc(
+        _p(x), NB, H, W, Cin, _p(x2), C2, _p(wp), cout, len(taps), dy, dx, stride, Ho, Wo,
+        out_mul, out_off[0], out_off[1], _p(bias), _p(rowvec),
+        rowvec.stride(0) if rowvec is not None else 0, _p(residual), _p(out),
+        int(out.dtype == F32), int(out_nchw), act, _stream())
+    _lib.check(rc, "b200_conv2d_nhwc")
+    return out
+
+
+def im2col3x3(x_nchw, kpad):
+    _need_cuda(x_nchw)
+    assert x_nchw.is_contiguous() and x_nchw.dtype in (F16, F32)
+    NB, C, H, W = x_nchw.shape
+    out = torch.empty((NB * H * W, kpad), dtype=F16, device=x_nchw.device)
+    rc = _lib.load().b200_im2col3x3_nchw(_p(x_nchw), int(x_nchw.dtype == F32), NB, C, H, W, _p(out), kpad, _stream())
+    _lib.check(rc, "b200_im2col3x3_nchw")
+    return out
+
+
+# ------------------------------------------------------------------------------ norms
+def group_norm(x1, gamma, beta, eps, groups=32, silu=True, x2=None, want_raw=False):
+    """NHWC (fp16 or fp32) -> normalised fp16 NHWC of the channel-concat [x1 | x2]."""
+    _need_cuda(x1, x2)
+    assert x1.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.dtype == x1.dtype))
+    NB, H, W, C1 = x1.shape
+    C2 = x2.shape[3] if x2 is not None else 0
+    C = C1 + C2
+    f32 = int(x1.dtype == F32)
+    sums = torch.zeros((NB, groups, 2), dtype=torch.float64, device=x1.device)
+    L = _lib.load()
+    _lib.check(L.b200_group_norm_stats(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _stream()),
+               "b200_group_norm_stats")
+    y = torch.empty((NB, H, W, C), dtype=F16, device=x1.device)
+    raw = torch.empty_like(y) if want_raw else None
+    _lib.check(L.b200_group_norm_apply(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _p(gamma),
+                                       _p(beta), float(eps), int(silu), _p(y), _p(raw), _stream()),
+               "b200_group_norm_apply")
+    return (y, raw) if want_raw else y
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    _need_cuda(x)
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty(x.shape, dtype=F16, device=x.device)
+    _lib.check(_lib.load().b200_layer_norm(_p(x), int(x.dtype == F32), rows, C, _p(gamma), _p(beta), float(eps),
+                                           _p(y), _stream()), "b200_layer_norm")
+    return y
+
+
+# ------------------------------------------------------------------------------ attention
+def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None):
+    """q: [B,Lq,>=heads*64] view, k/v: [B,Lk,...] views (fp16, last dim contiguous) -> [B,Lq,heads*64]."""
+    _need_cuda(q, k, v)
+    assert q.dtype == F16 and k.dtype == F16 and v.dtype == F16
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
+    B, Lq = q.shape[0], q.shape[1]
+    Lk = k.shape[1]
+    if out is None:
+        out = torch.empty((B, Lq, heads * 64), dtype=F16, device=q.device)
+    kb = k.stride(0) if k.shape[0] > 1 else k.stride(1) * Lk
+    vb = v.stride(0) if v.shape[0] > 1 else v.stride(1) * Lk
+    qb = q.stride(0) if B > 1 else q.stride(1) * Lq
+    rc = _lib.load().b200_attention_d64(_p(q), qb, q.stride(1), _p(k), kb, k.stride(1), _p(v), vb, v.stride(1),
+                                        _p(out), out.stride(0) if B > 1 else out.stride(1) * Lq, out.stride(1),
+                                        B, heads, Lq, Lk, kv_segments, float(scale), _stream())
+    _lib.check(rc, "b200_attention_d64")
+    return out
+
+
+def softmax_rows(s, scale, cols=None):
+    """softmax(scale*s) over the last dim -> fp16, same (possibly padded) layout.  `cols` = valid
+    columns when the last dim is padded (row stride = s.shape[-1])."""
+    _need_cuda(s)
+    assert s.dtype == F32 and s.is_contiguous()
+    ld = s.shape[-1]
+    cols = cols or ld
+    rows = s.numel() // ld
+    p = torch.empty(s.shape, dtype=F16, device=s.device)
+    _lib.check(_lib.load().b200_softmax_rows(_p(s), ld, _p(p), ld, rows, cols, float(scale), _stream()),
+               "b200_softmax_rows")
+    return p
+
+
+# ------------------------------------------------------------------------------ elementwise
+def upsample_nearest(x, out_hw):
+    _need_cuda(x)
+    assert x.is_contiguous()
+    NB, H, W, C = x.shape
+    OH, OW = out_hw
+    y = torch.empty((NB, OH, OW, C), dtype=F16, device=x.device)
+    _lib.check(_lib.load().b200_upsample_nearest_nhwc(_p(x), int(x.dtype == F32), NB, H, W, C, OH, OW, _p(y),
+                                                      _stream()), "b200_upsample_nearest_nhwc")
+    return y
+
+
+def timestep_embedding(t, dim):
+    _need_cuda(t)
+    assert t.dtype == F32 and t.is_contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=F16, device=t.device)
+    _lib.check(_lib.load().b200_timestep_embedding(_p(t), t.shape[0], dim, _p(out), _stream()),
+               "b200_timestep_embedding")
+    return out
+
+
+def pointwise_nchw(in1, a1, wm, bias, in2=None, a2=0.0, cin=None):
+    """out[n,co] = sum_ci wm[co,ci]*(a1*in1[n,ci] + a2*in2[n,ci]) + bias[co]; fp32 NCHW, C<=8."""
+    _need_cuda(in1)
+    assert in1.dtype == F32 and in1.is_contiguous() and (in2 is None or (in2.dtype == F32 and in2.is_contiguous()))
+    NB, Cs, H, W = in1.shape
+    cout, cin_ = wm.shape
+    cin = cin or cin_
+    out = torch.empty((NB, cout, H, W), dtype=F32, device=in1.device)
+    _lib.check(_lib.load().b200_pointwise_nchw(_p(in1), float(a1), _p(in2), float(a2), Cs, _p(wm), _p(bias), NB,
+                                               cin, cout, H * W, _p(out), _stream()), "b200_pointwise_nchw")
+    return out
+
+
+def decode_post(x, normals=False, sign=1.0):
+    _need_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.shape[1] == 3
+    NB, _, H, W = x.shape
+    out = torch.empty((NB, 3 if normals else 1, H, W), dtype=F32, device=x.device)
+    _lib.check(_lib.load().b200_decode_post(_p(x), NB, H * W, int(normals), float(sign), _p(out), _stream()),
+               "b200_decode_post")
+    return out
+
+
+def cast_f16(x):
+    _need_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous()
+    y = torch.empty(x.shape, dtype=F16, device=x.device)
+    _lib.check(_lib.load().b200_cast_f32_to_f16(_p(x), _p(y), x.numel(), _stream()), "b200_cast_f32_to_f16")
+    return y
+
+
+def nhwc_to_nchw_f32(x):
+    _need_cuda(x)
+    assert x.is_contiguous()
+    NB, H, W, C = x.shape
+    y = torch.empty((NB, C, H, W), dtype=F32, device=x.device)
+    _lib.check(_lib.load().b200_nhwc_to_nchw_f32(_p(x), int(x.dtype == F32), NB, C, H * W, _p(y), _stream()),
+               "b200_nhwc_to_nchw_f32")
+    return y

@@ -47,6 +47,10 @@ int b200_linear(const void* A, long long lda, long long a_batch_stride,
                 void* out, long long ldo, long long out_batch_stride, int out_f32,
                 int act, float alpha, void* stream);
 
+/* GEGLU tile width for packed width N (weights/bias rows are interleaved per tile of this width:
+ * [value rows of the tile | gate rows of the tile]); 0 = not tileable. */
+int b200_geglu_block_n(int N);
+
 /* Implicit-GEMM convolution on NHWC fp16 input, weights packed [Cout][tap][Cin] (+[C2] shortcut
  * columns), tcgen05 + TMA, no im2col buffer.  Tap t reads input pixel
  * (ho*stride + tap_dy[t], wo*stride + tap_dx[t]); out-of-range pixels read as zero (padding).

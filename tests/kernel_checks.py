@@ -1,0 +1,273 @@
+"""Kernel-level parity checks (CUDA kernel through the C ABI vs a plain PyTorch fp32 reference of
+the same op on the same seeded inputs).  Used by tests/test_kernels_gpu.py (pytest -m gpu) and by
+tools/gpu_kernel_check.py (one subprocess per check, so one broken kernel cannot hide the others).
+
+Tolerances: operands are fp16-rounded before BOTH paths, accumulation is fp32 on both, so the
+residual error is summation order + fp16 output rounding: rel-L2 <= 2e-3 (fp16 out) / 2e-5-ish
+(fp32 out).  Written per check below.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from diffusion_e2e_ft_b200 import ops
+
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _rand(*shape, seed=0, scale=1.0, dtype=torch.float16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+# ----------------------------------------------------------------------------------- GEMM
+def check_linear(M=300, N=320, K=320, bias=True, residual=False, out_f32=False, act=0, batch=0, seed=0,
+                 tol=None):
+    bs = (batch,) if batch else ()
+    a = _rand(*bs, M, K, seed=seed, scale=1.0)
+    w = _rand(*bs, N, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
+    b = _rand(N, seed=seed + 2, dtype=torch.float32) if bias else None
+    odt = torch.float32 if out_f32 else torch.float16
+    n_out = N // 2 if act == ops.ACT_GEGLU else N
+    r = _rand(*bs, M, n_out, seed=seed + 3, dtype=odt) if residual else None
+    ref = torch.matmul(a.float(), w.float().transpose(-1, -2))
+    if b is not None:
+        ref = ref + b
+    if act == ops.ACT_GEGLU:
+        h, g = ref.chunk(2, dim=-1)
+        ref = h * F.gelu(g)
+        wp, bp = ops.pack_geglu(w, b)
+    else:
+        wp, bp = w, b
+    if r is not None:
+        ref = ref + r.float()
+    if act == ops.ACT_SILU:
+        ref = F.silu(ref)
+    out = ops.linear(a, wp, bp, residual=r, out_dtype=odt, act=act)
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    tol = tol or (3e-5 if out_f32 else 1e-3)
+    return err, tol
+
+
+def check_linear_bias_row(seed=5):
+    """D[m,n] = W[m,:]·h[n,:] + bias[m]  (V^T projection of the VAE attention)."""
+    M, N, K = 512, 700, 512
+    a = _rand(M, K, seed=seed, scale=1 / math.sqrt(K))
+    w = _rand(N, K, seed=seed + 1)
+    b = _rand(M, seed=seed + 2, dtype=torch.float32)
+    ref = a.float() @ w.float().t() + b[:, None]
+    out = ops.linear(a, w, b, bias_row=True)
+    torch.cuda.synchronize()
+    return rel_l2(out, ref), 1e-3
+
+
+# ----------------------------------------------------------------------------------- conv
+def _conv_ref(x_nhwc, w, b, stride, pad_mode):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    if pad_mode == "vae_down":
+        x = F.pad(x, (0, 1, 0, 1))
+        return F.conv2d(x, w.float(), b, stride=stride, padding=0)
+    return F.conv2d(x, w.float(), b, stride=stride, padding=1)
+
+
+def check_conv(NB=2, H=24, W=24, Cin=128, Cout=192, stride=1, pad_mode="same", shortcut=0, rowvec=False,
+               residual=False, out_f32=False, out_nchw=False, seed=0, tol=None):
+    x = _rand(NB, H, W, Cin, seed=seed)
+    w = _rand(Cout, Cin, 3, 3, seed=seed + 1, scale=1.0 / math.sqrt(9 * Cin))
+    b = _rand(Cout, seed=seed + 2, dtype=torch.float32)
+    ref = _conv_ref(x, w, b, stride, pad_mode)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    x2 = ws = None
+    if shortcut:
+        x2 = _rand(NB, Ho, Wo, shortcut, seed=seed + 4)
+        ws = _rand(Cout, shortcut, 1, 1, seed=seed + 5, scale=1.0 / math.sqrt(shortcut))
+        ref = ref + F.conv2d(x2.float().permute(0, 3, 1, 2), ws.float())
+    rv = None
+    if rowvec:
+        rv = _rand(NB, Cout, seed=seed + 6, dtype=torch.float32)
+        ref = ref + rv[:, :, None, None]
+    odt = torch.float32 if out_f32 else torch.float16
+    res = None
+    if residual:
+        res = _rand(NB, Ho, Wo, Cout, seed=seed + 7, dtype=odt)
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    wp = ops.pack_conv(w, ws)
+    taps = ops.TAPS3_PAD0 if pad_mode == "vae_down" else ops.TAPS3
+    out = ops.conv2d(x, wp, Cout, bias=b, taps=taps, stride=stride, out_hw=(Ho, Wo), x2=x2, rowvec=rv,
+                     residual=res, out_dtype=odt, out_nchw=out_nchw)
+    torch.cuda.synchronize()
+    got = out if out_nchw else out.permute(0, 3, 1, 2)
+    err = rel_l2(got, ref)
+    return err, tol or (3e-5 if out_f32 else 1e-3)
+
+
+def check_conv_in(NB=2, C=8, H=20, W=24, Cout=320, seed=3):
+    """small-Cin conv = im2col kernel + GEMM, NCHW fp32 input straight from the caller."""
+    x = _rand(NB, C, H, W, seed=seed, dtype=torch.float32)
+    w = _rand(Cout, C, 3, 3, seed=seed + 1, scale=1.0 / math.sqrt(9 * C))
+    b = _rand(Cout, seed=seed + 2, dtype=torch.float32)
+    kpad = (9 * C + 7) // 8 * 8
+    patches = ops.im2col3x3(x, kpad)
+    out = ops.linear(patches, ops.pack_conv_small_cin(w, kpad), b)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.half().float(), w.half().float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    return rel_l2(out, ref), 1e-3
+
+
+# ----------------------------------------------------------------------------------- norms
+def check_group_norm(NB=2, H=17, W=24, C1=320, C2=0, in_f32=False, silu=True, seed=0):
+    dt = torch.float32 if in_f32 else torch.float16
+    x1 = _rand(NB, H, W, C1, seed=seed, dtype=dt) + 0.5
+    x2 = (_rand(NB, H, W, C2, seed=seed + 1, dtype=dt) * 2.0) if C2 else None
+    C = C1 + C2
+    g = _rand(C, seed=seed + 2, dtype=torch.float32) * 0.2 + 1.0
+    b = _rand(C, seed=seed + 3, dtype=torch.float32) * 0.2
+    y, raw = ops.group_norm(x1, g, b, 1e-5, 32, silu, x2=x2, want_raw=True)
+    torch.cuda.synchronize()
+    xc = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
+    ref = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    e1 = rel_l2(y, ref)
+    e2 = rel_l2(raw, xc)
+    return max(e1, e2), 6e-4
+
+
+def check_layer_norm(rows=1000, C=640, in_f32=True, seed=0):
+    dt = torch.float32 if in_f32 else torch.float16
+    x = _rand(rows, C, seed=seed, dtype=dt) * 2 + 0.3
+    g = _rand(C, seed=seed + 2, dtype=torch.float32) * 0.2 + 1.0
+    b = _rand(C, seed=seed + 3, dtype=torch.float32) * 0.2
+    y = ops.layer_norm(x, g, b, 1e-5)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    return rel_l2(y, ref), 6e-4
+
+
+def check_softmax_rows(rows=300, cols=1152, seed=0):
+    s = _rand(rows, cols, seed=seed, dtype=torch.float32) * 20
+    p = ops.softmax_rows(s, 0.125)
+    torch.cuda.synchronize()
+    return rel_l2(p, torch.softmax(s * 0.125, dim=-1)), 6e-4
+
+
+# ----------------------------------------------------------------------------------- attention
+def check_attention(B=2, heads=5, Lq=576, Lk=None, joint=False, gain=3.0, seed=0):
+    Lk = Lk or Lq
+    C = heads * 64
+    qkv = _rand(B, Lq, 3 * C, seed=seed)
+    if Lk == Lq:
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:
+        q = qkv[..., :C]
+        kv = _rand(B, Lk, 2 * C, seed=seed + 1)
+        k, v = kv[..., :C], kv[..., C:]
+    q = q * gain if False else q
+    scale = 64 ** -0.5 * gain
+    out = ops.attention_d64(q, k, v, heads, scale, kv_segments=2 if joint else 1)
+    torch.cuda.synchronize()
+    qf = q.float().view(B, Lq, heads, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Lk, heads, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Lk, heads, 64).transpose(1, 2)
+    if joint:
+        k0, k1 = kf.chunk(2, 0)
+        v0, v1 = vf.chunk(2, 0)
+        kf = torch.cat([torch.cat([k0, k1], 2)] * 2, 0)
+        vf = torch.cat([torch.cat([v0, v1], 2)] * 2, 0)
+    p = torch.softmax(qf @ kf.transpose(-1, -2) * scale, dim=-1)
+    ref = (p @ vf).transpose(1, 2).reshape(B, Lq, C)
+    return rel_l2(out, ref), 2e-3
+
+
+# ----------------------------------------------------------------------------------- elementwise
+def check_upsample(in_f32=False, out_hw=None):
+    dt = torch.float32 if in_f32 else torch.float16
+    x = _rand(2, 7, 9, 64, dtype=dt)
+    ohw = out_hw or (14, 18)
+    y = ops.upsample_nearest(x, ohw)
+    torch.cuda.synchronize()
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=ohw, mode="nearest").permute(0, 2, 3, 1)
+    return rel_l2(y, ref.half()), 1e-6
+
+
+def check_timestep_embedding():
+    t = torch.tensor([999.0, 1.0, 500.0], device=DEV)
+    out = ops.timestep_embedding(t, 320)
+    torch.cuda.synchronize()
+    half = 160
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=DEV) / half)
+    e = t[:, None] * f[None]
+    ref = torch.cat([torch.cos(e), torch.sin(e)], -1)
+    return (out.float() - ref).abs().max().item(), 2e-3
+
+
+def check_pointwise_and_post():
+    x = _rand(2, 8, 6, 10, dtype=torch.float32)
+    z = _rand(2, 8, 6, 10, seed=9, dtype=torch.float32)
+    wm = _rand(4, 8, seed=3, dtype=torch.float32)
+    b = _rand(4, seed=4, dtype=torch.float32)
+    out = ops.pointwise_nchw(x, 0.5, wm, b, in2=z, a2=-2.0)
+    ref = torch.einsum("oc,nchw->nohw", wm, 0.5 * x - 2.0 * z) + b[None, :, None, None]
+    e1 = rel_l2(out, ref)
+    d = _rand(2, 3, 5, 7, seed=11, dtype=torch.float32)
+    dep = ops.decode_post(d, normals=False)
+    e2 = rel_l2(dep, (d.mean(1, keepdim=True).clip(-1, 1) + 1) / 2)
+    nrm = ops.decode_post(d, normals=True, sign=-1.0)
+    e3 = rel_l2(nrm, -d / (d.norm(dim=1, keepdim=True) + 1e-5))
+    y = _rand(2, 5, 6, 24, seed=12)
+    e4 = rel_l2(ops.nhwc_to_nchw_f32(y), y.float().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    return max(e1, e2, e3, e4), 1e-5
+
+
+CHECKS = {
+    "linear_basic": lambda: check_linear(),
+    "linear_small_m": lambda: check_linear(M=8, N=1280, K=320),
+    "linear_bn256": lambda: check_linear(M=2000, N=1280, K=1280, seed=2),
+    "linear_ragged_k": lambda: check_linear(M=130, N=64, K=72, seed=3),
+    "linear_f32_residual": lambda: check_linear(M=1000, N=640, K=2560, residual=True, out_f32=True),
+    "linear_f16_residual_silu": lambda: check_linear(M=257, N=1280, K=1280, residual=True, act=ops.ACT_SILU),
+    "linear_geglu": lambda: check_linear(M=300, N=2560, K=320, act=ops.ACT_GEGLU),
+    "linear_geglu_small": lambda: check_linear(M=100, N=512, K=64, act=ops.ACT_GEGLU),
+    "linear_batched": lambda: check_linear(M=200, N=300 // 4 * 4 + 4, K=512, batch=3, bias=False),
+    "linear_bias_row": check_linear_bias_row,
+    "linear_unaligned_ldo": lambda: check_linear(M=130, N=700, K=128, residual=True, seed=7),
+    "conv_s1": lambda: check_conv(),
+    "conv_s1_96": lambda: check_conv(NB=1, H=96, W=96, Cin=64, Cout=320),
+    "conv_s1_odd": lambda: check_conv(NB=1, H=15, W=20, Cin=64, Cout=64),
+    "conv_s1_12": lambda: check_conv(NB=3, H=12, W=12, Cin=256, Cout=256),
+    "conv_fused_shortcut_temb_res_f32": lambda: check_conv(shortcut=64, rowvec=True, residual=True, out_f32=True),
+    "conv_res_f16": lambda: check_conv(residual=True),
+    "conv_s2_pad1": lambda: check_conv(stride=2),
+    "conv_s2_pad1_odd": lambda: check_conv(H=15, W=30, stride=2, Cin=64, Cout=64),
+    "conv_s2_vae": lambda: check_conv(stride=2, pad_mode="vae_down", H=32, W=48),
+    "conv_out_nchw": lambda: check_conv(Cin=128, Cout=3, out_f32=True, out_nchw=True, H=40, W=56),
+    "conv_out4_nchw": lambda: check_conv(Cin=64, Cout=4, out_f32=True, out_nchw=True),
+    "conv_in_im2col": check_conv_in,
+    "gn_f16": lambda: check_group_norm(),
+    "gn_f32_concat": lambda: check_group_norm(C1=1280, C2=640, in_f32=True),
+    "gn_concat_f16_nosilu": lambda: check_group_norm(C1=640, C2=320, silu=False),
+    "gn_128": lambda: check_group_norm(C1=128, H=64, W=64),
+    "ln_f32": lambda: check_layer_norm(),
+    "ln_f16_1280": lambda: check_layer_norm(C=1280, in_f32=False),
+    "ln_320": lambda: check_layer_norm(C=320),
+    "softmax_rows": check_softmax_rows,
+    "attn_self_576": lambda: check_attention(),
+    "attn_self_2304": lambda: check_attention(B=1, heads=10, Lq=2304),
+    "attn_ragged_144": lambda: check_attention(B=2, heads=20, Lq=144),
+    "attn_cross_2": lambda: check_attention(Lq=576, Lk=2),
+    "attn_cross_77": lambda: check_attention(Lq=300, Lk=77),
+    "attn_joint": lambda: check_attention(B=4, heads=5, Lq=576, joint=True),
+    "upsample_2x": check_upsample,
+    "upsample_size_f32": lambda: check_upsample(True, (15, 20)),
+    "timestep_embedding": check_timestep_embedding,
+    "pointwise_post": check_pointwise_and_post,
+}
