@@ -17,6 +17,38 @@ TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]        # pad=1
 TAPS3_PAD0 = [(ky, kx) for ky in range(3) for kx in range(3)]           # VAE downsample (0,1,0,1) pad
 
 
+class Stats:
+    """Launch / algorithmic-FLOP accounting (2*MAC, tensor-pipe ops only: SURVEY.md App. B rules) and
+    optional CUDA-event timing of the implicit-GEMM conv launches (bench.py's roofline leg)."""
+
+    def __init__(self):
+        self.reset()
+        self.time_kind = None          # e.g. "conv": bracket those launches with CUDA events
+
+    def reset(self):
+        self.launches = 0
+        self.flops = {"conv": 0, "linear": 0, "attn": 0}
+        self.count = {"conv": 0, "linear": 0, "attn": 0}
+        self.events = []               # (start, end, flops)
+
+    def add(self, kind=None, flops=0):
+        self.launches += 1
+        if kind is not None:
+            self.flops[kind] += flops
+            self.count[kind] += 1
+
+    def timed(self, kind):
+        return self.time_kind == kind
+
+
+STATS = Stats()
+
+
+def _ck(rc, what):
+    _lib.check(rc, what)
+    STATS.add()
+
+
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -96,6 +128,7 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
         _p(out), out.stride(-2), out.stride(0) if batched else 0, int(out.dtype == F32),
         act, float(alpha), _stream())
     _lib.check(rc, "b200_linear")
+    STATS.add("linear", 2 * B * M * N * K)
     return out
 
 
@@ -120,12 +153,21 @@ def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, r
         assert residual.dtype == out.dtype and residual.is_contiguous() and residual.shape == out.shape
     dy = (c_int * len(taps))(*[t[0] for t in taps])
     dx = (c_int * len(taps))(*[t[1] for t in taps])
+    fl = 2 * NB * Ho * Wo * cout * (len(taps) * Cin + C2)
+    ev = None
+    if STATS.timed("conv"):
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     rc = _lib.load().b200_conv2d_nhwc(
         _p(x), NB, H, W, Cin, _p(x2), C2, _p(wp), cout, len(taps), dy, dx, stride, Ho, Wo,
         out_mul, out_off[0], out_off[1], _p(bias), _p(rowvec),
         rowvec.stride(0) if rowvec is not None else 0, _p(residual), _p(out),
         int(out.dtype == F32), int(out_nchw), act, _stream())
     _lib.check(rc, "b200_conv2d_nhwc")
+    if ev is not None:
+        ev[1].record()
+        STATS.events.append((ev[0], ev[1], fl, (NB, H, W, Cin, C2, cout, len(taps), stride, str(out.dtype)[6:])))
+    STATS.add("conv", fl)
     return out
 
 
@@ -135,7 +177,7 @@ def im2col3x3(x_nchw, kpad):
     NB, C, H, W = x_nchw.shape
     out = torch.empty((NB * H * W, kpad), dtype=F16, device=x_nchw.device)
     rc = _lib.load().b200_im2col3x3_nchw(_p(x_nchw), int(x_nchw.dtype == F32), NB, C, H, W, _p(out), kpad, _stream())
-    _lib.check(rc, "b200_im2col3x3_nchw")
+    _ck(rc, "b200_im2col3x3_nchw")
     return out
 
 
@@ -150,11 +192,11 @@ def group_norm(x1, gamma, beta, eps, groups=32, silu=True, x2=None, want_raw=Fal
     f32 = int(x1.dtype == F32)
     sums = torch.zeros((NB, groups, 2), dtype=torch.float64, device=x1.device)
     L = _lib.load()
-    _lib.check(L.b200_group_norm_stats(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _stream()),
+    _ck(L.b200_group_norm_stats(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _stream()),
                "b200_group_norm_stats")
     y = torch.empty((NB, H, W, C), dtype=F16, device=x1.device)
     raw = torch.empty_like(y) if want_raw else None
-    _lib.check(L.b200_group_norm_apply(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _p(gamma),
+    _ck(L.b200_group_norm_apply(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _p(gamma),
                                        _p(beta), float(eps), int(silu), _p(y), _p(raw), _stream()),
                "b200_group_norm_apply")
     return (y, raw) if want_raw else y
@@ -166,7 +208,7 @@ def layer_norm(x, gamma, beta, eps=1e-5):
     C = x.shape[-1]
     rows = x.numel() // C
     y = torch.empty(x.shape, dtype=F16, device=x.device)
-    _lib.check(_lib.load().b200_layer_norm(_p(x), int(x.dtype == F32), rows, C, _p(gamma), _p(beta), float(eps),
+    _ck(_lib.load().b200_layer_norm(_p(x), int(x.dtype == F32), rows, C, _p(gamma), _p(beta), float(eps),
                                            _p(y), _stream()), "b200_layer_norm")
     return y
 
@@ -188,6 +230,7 @@ def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None):
                                         _p(out), out.stride(0) if B > 1 else out.stride(1) * Lq, out.stride(1),
                                         B, heads, Lq, Lk, kv_segments, float(scale), _stream())
     _lib.check(rc, "b200_attention_d64")
+    STATS.add("attn", 4 * B * heads * Lq * Lk * kv_segments * 64)
     return out
 
 
@@ -200,7 +243,7 @@ def softmax_rows(s, scale, cols=None):
     cols = cols or ld
     rows = s.numel() // ld
     p = torch.empty(s.shape, dtype=F16, device=s.device)
-    _lib.check(_lib.load().b200_softmax_rows(_p(s), ld, _p(p), ld, rows, cols, float(scale), _stream()),
+    _ck(_lib.load().b200_softmax_rows(_p(s), ld, _p(p), ld, rows, cols, float(scale), _stream()),
                "b200_softmax_rows")
     return p
 
@@ -212,7 +255,7 @@ def upsample_nearest(x, out_hw):
     NB, H, W, C = x.shape
     OH, OW = out_hw
     y = torch.empty((NB, OH, OW, C), dtype=F16, device=x.device)
-    _lib.check(_lib.load().b200_upsample_nearest_nhwc(_p(x), int(x.dtype == F32), NB, H, W, C, OH, OW, _p(y),
+    _ck(_lib.load().b200_upsample_nearest_nhwc(_p(x), int(x.dtype == F32), NB, H, W, C, OH, OW, _p(y),
                                                       _stream()), "b200_upsample_nearest_nhwc")
     return y
 
@@ -221,7 +264,7 @@ def timestep_embedding(t, dim):
     _need_cuda(t)
     assert t.dtype == F32 and t.is_contiguous()
     out = torch.empty((t.shape[0], dim), dtype=F16, device=t.device)
-    _lib.check(_lib.load().b200_timestep_embedding(_p(t), t.shape[0], dim, _p(out), _stream()),
+    _ck(_lib.load().b200_timestep_embedding(_p(t), t.shape[0], dim, _p(out), _stream()),
                "b200_timestep_embedding")
     return out
 
@@ -234,7 +277,7 @@ def pointwise_nchw(in1, a1, wm, bias, in2=None, a2=0.0, cin=None):
     cout, cin_ = wm.shape
     cin = cin or cin_
     out = torch.empty((NB, cout, H, W), dtype=F32, device=in1.device)
-    _lib.check(_lib.load().b200_pointwise_nchw(_p(in1), float(a1), _p(in2), float(a2), Cs, _p(wm), _p(bias), NB,
+    _ck(_lib.load().b200_pointwise_nchw(_p(in1), float(a1), _p(in2), float(a2), Cs, _p(wm), _p(bias), NB,
                                                cin, cout, H * W, _p(out), _stream()), "b200_pointwise_nchw")
     return out
 
@@ -244,7 +287,7 @@ def decode_post(x, normals=False, sign=1.0):
     assert x.dtype == F32 and x.is_contiguous() and x.shape[1] == 3
     NB, _, H, W = x.shape
     out = torch.empty((NB, 3 if normals else 1, H, W), dtype=F32, device=x.device)
-    _lib.check(_lib.load().b200_decode_post(_p(x), NB, H * W, int(normals), float(sign), _p(out), _stream()),
+    _ck(_lib.load().b200_decode_post(_p(x), NB, H * W, int(normals), float(sign), _p(out), _stream()),
                "b200_decode_post")
     return out
 
@@ -253,7 +296,7 @@ def cast_f16(x):
     _need_cuda(x)
     assert x.dtype == F32 and x.is_contiguous()
     y = torch.empty(x.shape, dtype=F16, device=x.device)
-    _lib.check(_lib.load().b200_cast_f32_to_f16(_p(x), _p(y), x.numel(), _stream()), "b200_cast_f32_to_f16")
+    _ck(_lib.load().b200_cast_f32_to_f16(_p(x), _p(y), x.numel(), _stream()), "b200_cast_f32_to_f16")
     return y
 
 
@@ -262,6 +305,6 @@ def nhwc_to_nchw_f32(x):
     assert x.is_contiguous()
     NB, H, W, C = x.shape
     y = torch.empty((NB, C, H, W), dtype=F32, device=x.device)
-    _lib.check(_lib.load().b200_nhwc_to_nchw_f32(_p(x), int(x.dtype == F32), NB, C, H * W, _p(y), _stream()),
+    _ck(_lib.load().b200_nhwc_to_nchw_f32(_p(x), int(x.dtype == F32), NB, C, H * W, _p(y), _stream()),
                "b200_nhwc_to_nchw_f32")
     return y

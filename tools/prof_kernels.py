@@ -1,0 +1,42 @@
+"""Tiny launcher for ncu captures of single kernels at production shapes.
+    python tools/prof_kernels.py conv128|conv320|conv1280|attn|gn|linear"""
+import os, sys, math
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from diffusion_e2e_ft_b200 import ops
+what = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = "cuda"
+g = torch.Generator(device="cpu").manual_seed(0)
+r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).half().to(dev)
+if what.startswith("conv"):
+    cfg = {"conv128": (4, 768, 768, 128, 128), "conv256": (8, 384, 384, 256, 256), "conv512": (8, 192, 192, 512, 512),
+           "conv320": (8, 96, 96, 320, 320), "conv640": (8, 48, 48, 640, 640), "conv1280": (8, 24, 24, 1280, 1280),
+           "conv1280s": (8, 12, 12, 1280, 1280), "conv2560": (8, 24, 24, 2560, 1280)}[what]
+    NB, H, W, Cin, Cout = cfg
+    x = r(NB, H, W, Cin); w = ops.pack_conv(r(Cout, Cin, 3, 3, sc=1 / math.sqrt(9 * Cin))); b = torch.zeros(Cout, device=dev)
+    fn = lambda: ops.conv2d(x, w, Cout, bias=b)
+    flops = 2 * NB * H * W * Cout * 9 * Cin
+elif what == "attn":
+    qkv = r(8, 9216, 960)
+    fn = lambda: ops.attention_d64(qkv[..., :320], qkv[..., 320:640], qkv[..., 640:], 5, 0.125)
+    flops = 4 * 8 * 5 * 9216 * 9216 * 64
+elif what == "gn":
+    x = r(4, 768, 768, 128); gm = torch.ones(128, device=dev); bt = torch.zeros(128, device=dev)
+    fn = lambda: ops.group_norm(x, gm, bt, 1e-6)
+    flops = 0
+elif what == "linear":
+    a = r(73728, 320); w = r(2560, 320, sc=0.05); b = torch.zeros(2560, device=dev)
+    fn = lambda: ops.linear(a, w, b)
+    flops = 2 * 73728 * 320 * 2560
+for _ in range(2):
+    fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    fn()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"{what}: {ms:.3f} ms/iter  {flops / ms / 1e9:.1f} TFLOP/s")
