@@ -1,13 +1,16 @@
 // Flash attention for head_dim 64 on sm_100a: softmax(Q K^T * scale) V, no mask.
 //
-// Warp-specialised: warp0 = TMA producer (Q once, K/V tiles through a 4-stage smem ring),
-// warp1 = tcgen05 issuer, warps 2..5 = softmax (one query row per thread — the TMEM lane layout
-// gives each thread its own row, so row max / row sum need no shuffles).
-//   S_j = Q K_j^T        tcgen05.mma  M128 N128 K64   -> TMEM (double buffered)
-//   P_j = exp2(S_j*c - m_j*c)  fp32 in registers -> fp16 into smem (SWIZZLE_128B, K-major A operand)
-//   T_j = P_j V_j        tcgen05.mma  M128 N64  K128  -> TMEM (double buffered), V consumed
-//                        MN-major straight from its [keys x d] TMA tile (no transpose)
-//   O   = O*alpha_j + T_j in registers (fp32), one tile late so it overlaps the next S/P.
+// Warp-specialised, 256 query rows per CTA: warp0 = TMA producer (two Q tiles once, K/V tiles through
+// a 3-stage smem ring), warp1 = tcgen05 issuer, warps 2..5 / 6..9 = two softmax warpgroups, each
+// owning one 128-row query tile with one row per thread (the TMEM lane layout gives each thread its
+// own row, so row max / row sum need no shuffles).  The two warpgroups ping-pong: while one runs its
+// exp pass (the MUFU-bound part at head_dim 64) the tensor core serves the other one.  Per tile j and
+// warpgroup w:
+//   S = Q_w K_j^T        tcgen05.mma  M128 N128 K64   -> TMEM
+//   P = exp2(S*c - m*c)  fp32 in registers -> fp16 into smem (SWIZZLE_128B, K-major A operand)
+//   T = P V_j            tcgen05.mma  M128 N64  K128  -> TMEM; V consumed MN-major straight from its
+//                        [keys x d] TMA tile (no transpose)
+//   O = O*alpha + T      in registers (fp32), folded in while the next S is already available.
 // Joint attention (GeoWizard): kv_segments = 2 walks the K/V tiles of batch b%(B/2) then
 // b%(B/2)+B/2 — the concatenated K/V of attention.py:482-491 is never materialised.
 #include "common.cuh"
@@ -15,14 +18,15 @@
 
 namespace b200 {
 
-constexpr int kAttThreads = 192;
-constexpr int kBq = 128;    // query rows per CTA
-constexpr int kBk = 128;    // keys per tile
+constexpr int kAttThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-5 softmax WG0, warps 6-9 softmax WG1
+constexpr int kBq = 128;           // query rows per softmax warpgroup (one row per thread)
+constexpr int kWG = 2;             // query tiles per CTA
+constexpr int kBk = 128;           // keys per tile
 constexpr int kD = 64;
-constexpr int kKvStages = 4;
+constexpr int kKvStages = 3;
 constexpr int kTileBytes = kBk * kD * 2;      // 16 KB (Q, K, V tiles)
 constexpr int kPBytes = kBq * kBk * 2;        // 32 KB
-constexpr int kAttSmem = kTileBytes + kKvStages * 2 * kTileBytes + 2 * kPBytes + 1024 + 1024;
+constexpr int kAttSmem = kWG * kTileBytes + kKvStages * 2 * kTileBytes + kWG * kPBytes + 1024 + 1024;
 
 struct AttParams {
   int B, heads, Lq, Lk, kv_segments;
@@ -31,29 +35,41 @@ struct AttParams {
   long long o_bs, o_ls;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
+  return r;
+}
+
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes;
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array itself, so
+  // the compiler keeps the shared address space (LDS/STS, no aliasing with global stores)
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                                   // [kWG][16 KB]
+  uint8_t* sK = sQ + kWG * kTileBytes;                  // [stages][16 KB]
   uint8_t* sV = sK + kKvStages * kTileBytes;
-  uint8_t* sP = sV + kKvStages * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint8_t* sP = sV + kKvStages * kTileBytes;            // [kWG][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kWG * kPBytes);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = k_full + kKvStages;
   uint64_t* kv_empty = v_full + kKvStages;
-  uint64_t* s_full = kv_empty + kKvStages;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_full = kv_empty + kKvStages;              // [kWG]
+  uint64_t* p_full = s_full + kWG;
+  uint64_t* o_full = p_full + kWG;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + kWG);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kBq;
+  const int q0 = blockIdx.x * (kWG * kBq);
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int tiles_per_seg = (p.Lk + kBk - 1) / kBk;
@@ -70,9 +86,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kWG; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], kBq);
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -82,13 +98,15 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tS = tmem_base;            // S0: [0,128)  S1: [128,256)
-  const uint32_t tO = tmem_base + 256;      // T0: [256,320) T1: [320,384)
+  const uint32_t tS = tmem_base;            // S[w]: columns [128w, 128w+128)
+  const uint32_t tO = tmem_base + 256;      // T[w]: columns [256+64w, 256+64w+64)
 
   if (warp == 0) {
+    // ===================================================================== TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_3d(&tmQ, q_full, sQ, h * kD, q0, b, kEvictFirst);
+      mbar_arrive_expect_tx(q_full, kWG * kTileBytes);
+      for (int w = 0; w < kWG; ++w)
+        tma_load_3d(&tmQ, q_full, sQ + w * kTileBytes, h * kD, q0 + w * kBq, b, kEvictFirst);
       int stage = 0;
       uint32_t phase = 0;
       for (int seg = 0; seg < p.kv_segments; ++seg) {
@@ -104,158 +122,192 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else if (warp == 1) {
+    // ===================================================================== tcgen05 issuer
     constexpr uint32_t idesc_qk = make_idesc_f16(kBq, kBk, 0, 0);
     constexpr uint32_t idesc_pv = make_idesc_f16(kBq, kD, 0, 1);   // B (=V) is MN-major
     mbar_wait(q_full, 0);
-    const uint64_t qdesc = make_desc_sw128(smem_u32(sQ), 16, 1024);
-    auto issue_qk = [&](int j) {
-      const int st = j % kKvStages;
-      mbar_wait(&k_full[st], (j / kKvStages) & 1);
-      tc_fence_after();
+    auto issue_qk = [&](int j, int w) {            // S[w] = Q[w] K_j^T
       if (lane == 0) {
+        const int st = j % kKvStages;
+        const uint64_t qdesc = make_desc_sw128(smem_u32(sQ + w * kTileBytes), 16, 1024);
         const uint64_t kdesc = make_desc_sw128(smem_u32(sK + st * kTileBytes), 16, 1024);
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k)
-          umma_f16(tS + (j & 1) * kBk, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[j & 1]);
+          umma_f16(tS + w * kBk, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[w]);
       }
       __syncwarp();
     };
-    issue_qk(0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(0, 1);
     for (int j = 0; j < n_tiles; ++j) {
-      if (j + 1 < n_tiles) issue_qk(j + 1);
       const int st = j % kKvStages;
-      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-      mbar_wait(&v_full[st], (j / kKvStages) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t pbase = smem_u32(sP + (j & 1) * kPBytes);
-        const uint32_t vbase = smem_u32(sV + st * kTileBytes);
+      for (int w = 0; w < kWG; ++w) {
+        mbar_wait(&p_full[w], j & 1);               // P[w](j) in smem, S[w] and T[w] drained by WG w
+        if (w == 0) mbar_wait(&v_full[st], (j / kKvStages) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t pbase = smem_u32(sP + w * kPBytes);
+          const uint32_t vbase = smem_u32(sV + st * kTileBytes);
 #pragma unroll
-        for (int k = 0; k < kBk / 16; ++k) {
-          // A = P[:, 16k..16k+16): K-major, two 64-key swizzle atoms of 16 KB each
-          const uint64_t pdesc = make_desc_sw128(pbase + (k >> 2) * (kBq * 128) + (k & 3) * 32, 16, 1024);
-          // B = V[16k..16k+16, :]: MN-major, 16 key rows = 2 groups of 8 rows (SBO = 1024 B)
-          const uint64_t vdesc = make_desc_sw128(vbase + k * 2048, 16, 1024);
-          umma_f16(tO + (j & 1) * kD, pdesc, vdesc, idesc_pv, k != 0);
+          for (int k = 0; k < kBk / 16; ++k) {
+            // A = P[:, 16k..16k+16): K-major, two 64-key swizzle atoms of 16 KB each
+            const uint64_t pdesc = make_desc_sw128(pbase + (k >> 2) * (kBq * 128) + (k & 3) * 32, 16, 1024);
+            // B = V[16k..16k+16, :]: MN-major, 16 key rows = 2 groups of 8 rows (SBO = 1024 B)
+            const uint64_t vdesc = make_desc_sw128(vbase + k * 2048, 16, 1024);
+            umma_f16(tO + w * kD, pdesc, vdesc, idesc_pv, k != 0);
+          }
+          umma_commit(&o_full[w]);
         }
-        umma_commit(&o_full[j & 1]);
-        umma_commit(&kv_empty[st]);
+        __syncwarp();
+        if (j + 1 < n_tiles) {
+          if (w == 0) {
+            mbar_wait(&k_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
+            tc_fence_after();
+          }
+          issue_qk(j + 1, w);
+        }
       }
+      if (lane == 0) umma_commit(&kv_empty[st]);     // K_j / V_j slot reusable once everything above retires
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ softmax / output warps
-    const int quad = warp & 3;
+    // ===================================================================== softmax warpgroups
+    const int w = (warp - 2) >> 2;                   // warpgroup: which 128-row query tile
+    const int quad = warp & 3;                       // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t ts = tS + w * kBk + lane_off;
+    const uint32_t to = tO + w * kD + lane_off;
     float o[kD];
 #pragma unroll
     for (int i = 0; i < kD; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
     const float c = p.scale_log2;
-    uint8_t* prow0 = sP + row * 128;
+    uint8_t* prow = sP + w * kPBytes + row * 128;
     const int sw = row & 7;
 
     for (int j = 0; j < n_tiles; ++j) {
       const int jj = j % tiles_per_seg;
       const int valid = min(kBk, p.Lk - jj * kBk);
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
-      const uint32_t ts = tS + (j & 1) * kBk + lane_off;
-      // pass 1: row max
-      float mx = -INFINITY;
+      // ---- pass 1: row max
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (valid == kBk) {
 #pragma unroll 1
-      for (int cc = 0; cc < kBk; cc += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(ts + cc, r);
-        tmem_ld_wait();
+        for (int cc = 0; cc < kBk; cc += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(ts + cc, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float v = (cc + e < valid) ? __uint_as_float(r[e]) : -INFINITY;
-          mx = fmaxf(mx, v);
-        }
-      }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f((m - m_new) * c);
-      const float mc = m_new * c;
-      // pass 2: probabilities -> smem (fp16), row sum
-      float rs = 0.f;
-      uint8_t* prow = prow0 + (j & 1) * kPBytes;
-#pragma unroll 1
-      for (int cc = 0; cc < kBk; cc += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(ts + cc, r);
-        tmem_ld_wait();
-        uint8_t* pchunk = prow + (cc >> 6) * (kBq * 128);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i0 = g * 8 + e * 2;
-            float p0 = (cc + i0 < valid) ? exp2f(__uint_as_float(r[i0]) * c - mc) : 0.f;
-            float p1 = (cc + i0 + 1 < valid) ? exp2f(__uint_as_float(r[i0 + 1]) * c - mc) : 0.f;
-            __half2 hh = __floats2half2_rn(p0, p1);
-            // accumulate the rounded values so the normaliser matches what the MMA consumes
-            float2 back = __half22float2(hh);
-            rs += back.x + back.y;
-            pk[e] = *reinterpret_cast<uint32_t*>(&hh);
+          for (int e = 0; e < 32; e += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(r[e]));
+            mx1 = fmaxf(mx1, __uint_as_float(r[e + 1]));
           }
-          const int chunk16 = ((cc & 63) >> 3) + g;      // logical 16-byte chunk within the 128-B row
-          *reinterpret_cast<uint4*>(pchunk + ((chunk16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < kBk; cc += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(ts + cc, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (cc + e < valid) mx0 = fmaxf(mx0, __uint_as_float(r[e]));
         }
       }
-      l = l * alpha + rs;
-      m = m_new;
-      tc_fence_before();          // our TMEM reads of S are done before the MMA warp may overwrite it
-      fence_proxy_async_smem();   // P visible to the tensor-core (async) proxy
-      mbar_arrive(&p_full[j & 1]);
-
+      const float m_new = fmaxf(m, fmaxf(mx0, mx1));
+      const float alpha = ex2_approx((m - m_new) * c);
+      const float mc = m_new * c;
+      // ---- fold the previous tile's P V product into O (T[w] must be drained before PV(j) is issued)
       if (j > 0) {
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        mbar_wait(&o_full[w], (j - 1) & 1);
         tc_fence_after();
-        const uint32_t to = tO + ((j - 1) & 1) * kD + lane_off;
 #pragma unroll
         for (int cc = 0; cc < kD; cc += 32) {
           uint32_t r[32];
           tmem_ld_32x32(to + cc, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) o[cc + e] = o[cc + e] * alpha_prev + __uint_as_float(r[e]);
+          for (int e = 0; e < 32; ++e) o[cc + e] = fmaf(o[cc + e], alpha_prev, __uint_as_float(r[e]));
         }
       }
+      // ---- pass 2: P = exp2(S*c - m*c) -> fp16 smem (SWIZZLE_128B K-major A operand), row sum
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < kBk; cc += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(ts + cc, r);
+        tmem_ld_wait();
+        uint8_t* pchunk = prow + (cc >> 6) * (kBq * 128);
+        if (valid == kBk) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i0 = g * 8 + e * 2;
+              const float p0 = ex2_approx(fmaf(__uint_as_float(r[i0]), c, -mc));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(r[i0 + 1]), c, -mc));
+              rs0 += p0;
+              rs1 += p1;
+              pk[e] = pack_half2(p0, p1);
+            }
+            const int chunk16 = ((cc & 63) >> 3) + g;    // logical 16-byte chunk within the 128-B row
+            *reinterpret_cast<uint4*>(pchunk + ((chunk16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i0 = g * 8 + e * 2;
+              const float p0 = (cc + i0 < valid) ? ex2_approx(fmaf(__uint_as_float(r[i0]), c, -mc)) : 0.f;
+              const float p1 = (cc + i0 + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(r[i0 + 1]), c, -mc)) : 0.f;
+              rs0 += p0;
+              rs1 += p1;
+              pk[e] = pack_half2(p0, p1);
+            }
+            const int chunk16 = ((cc & 63) >> 3) + g;
+            *reinterpret_cast<uint4*>(pchunk + ((chunk16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      l = fmaf(l, alpha, rs0 + rs1);
+      m = m_new;
       alpha_prev = alpha;
+      tc_fence_before();          // our TMEM reads (S[w], T[w]) are done before the MMA warp overwrites them
+      fence_proxy_async_smem();   // P visible to the tensor-core (async) proxy
+      mbar_arrive(&p_full[w]);
     }
     {
       const int j = n_tiles - 1;
-      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&o_full[w], j & 1);
       tc_fence_after();
-      const uint32_t to = tO + (j & 1) * kD + lane_off;
 #pragma unroll
       for (int cc = 0; cc < kD; cc += 32) {
         uint32_t r[32];
         tmem_ld_32x32(to + cc, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[cc + e] = o[cc + e] * alpha_prev + __uint_as_float(r[e]);
+        for (int e = 0; e < 32; ++e) o[cc + e] = fmaf(o[cc + e], alpha_prev, __uint_as_float(r[e]));
       }
     }
-    const int qrow = q0 + row;
+    const int qrow = q0 + w * kBq + row;
     if (qrow < p.Lq) {
       const float inv = 1.0f / l;
       __half* dst = p.out + (long long)b * p.o_bs + (long long)qrow * p.o_ls + h * kD;
 #pragma unroll
       for (int g = 0; g < kD; g += 8) {
-        __half2 h0 = __floats2half2_rn(o[g] * inv, o[g + 1] * inv);
-        __half2 h1 = __floats2half2_rn(o[g + 2] * inv, o[g + 3] * inv);
-        __half2 h2 = __floats2half2_rn(o[g + 4] * inv, o[g + 5] * inv);
-        __half2 h3 = __floats2half2_rn(o[g + 6] * inv, o[g + 7] * inv);
         uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        u.x = pack_half2(o[g] * inv, o[g + 1] * inv);
+        u.y = pack_half2(o[g + 2] * inv, o[g + 3] * inv);
+        u.z = pack_half2(o[g + 4] * inv, o[g + 5] * inv);
+        u.w = pack_half2(o[g + 6] * inv, o[g + 7] * inv);
         *reinterpret_cast<uint4*>(dst + g) = u;
       }
     }
@@ -316,7 +368,7 @@ extern "C" int b200_attention_d64(const void* q, long long q_bs, long long q_ls,
   p.B = B; p.heads = heads; p.Lq = Lq; p.Lk = Lk; p.kv_segments = kv_segments;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = (__half*)out; p.o_bs = o_bs; p.o_ls = o_ls;
-  dim3 grid((Lq + kBq - 1) / kBq, heads, B);
+  dim3 grid((Lq + kWG * kBq - 1) / (kWG * kBq), heads, B);
   attention_d64_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tq, tk, tv, p);
   B200_CHECK_LAUNCH("attention_d64_kernel");
   return 0;

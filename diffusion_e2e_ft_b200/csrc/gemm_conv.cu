@@ -138,6 +138,7 @@ static int pick_block_n(int N, long long m_tiles_total, int force) {
 }
 
 static int g_force_bn = 0;
+static int g_debug = 0;
 
 }  // namespace b200
 
@@ -145,6 +146,7 @@ using namespace b200;
 
 extern "C" const char* b200_last_error_string(void) { return b200::last_error(); }
 extern "C" void b200_debug_force_block_n(int bn) { b200::g_force_bn = bn; }
+extern "C" void b200_debug_set_flags(int f) { b200::g_debug = f; }
 extern "C" int b200_abi_version(void) { return 1; }
 // Tile width used by the GEGLU epilogue for a packed width N (= 2 x output width); weights must be
 // packed per tile as [value half | gate half] with this width.
@@ -168,6 +170,8 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   B200_CHECK_ARG(batch == 1 || (a_batch_stride % 8 == 0 && (w_batch_stride % 8 == 0)),
                  "b200_linear: batch strides must be multiples of 8 elements");
 
+  B200_CHECK_ARG((long long)M * ldo < 0xFFFFFFFFll && (long long)M * (ld_res > 0 ? ld_res : 1) < 0xFFFFFFFFll,
+                 "b200_linear: per-batch output larger than 2^32 elements");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N;
@@ -183,7 +187,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.out = out; p.ldo = ldo; p.out_batch_stride = out_batch_stride; p.out_f32 = out_f32;
   p.bias = bias; p.bias_row = bias_row;
   p.residual = residual; p.ld_res = ld_res; p.res_batch_stride = res_batch_stride;
-  p.act = act; p.alpha = alpha;
+  p.act = act; p.alpha = alpha; p.debug = g_debug;
   p.out_mul = 1;
   p.vec_ok = (ldo % 8 == 0) && (out_batch_stride % 8 == 0) &&
              (!residual || (ld_res % 8 == 0 && res_batch_stride % 8 == 0 && ((uintptr_t)residual & 15) == 0));
@@ -242,8 +246,10 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   B200_CHECK_ARG(((uintptr_t)X & 15) == 0 && ((uintptr_t)Wp & 15) == 0 && ((uintptr_t)out & 15) == 0,
                  "b200_conv2d_nhwc: pointers must be 16-byte aligned");
   B200_CHECK_ARG(act != ACT_GEGLU, "b200_conv2d_nhwc: GEGLU epilogue is linear-only");
-  B200_CHECK_ARG(!out_nchw || !residual, "b200_conv2d_nhwc: out_nchw excludes residual");
+  B200_CHECK_ARG(!out_nchw || (!residual && Cout <= 8), "b200_conv2d_nhwc: out_nchw needs Cout <= 8 and no residual");
 
+  B200_CHECK_ARG((long long)NB * Ho * out_mul * Wo * out_mul * Cout < 0xFFFFFFFFll,
+                 "b200_conv2d_nhwc: output larger than 2^32 elements");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.conv = 1;
@@ -268,7 +274,7 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   p.out = out; p.ldo = Cout; p.out_f32 = out_f32; p.out_nchw = out_nchw;
   p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec;
   p.residual = residual; p.ld_res = Cout;
-  p.act = act; p.alpha = 1.0f;
+  p.act = act; p.alpha = 1.0f; p.debug = g_debug;
   p.vec_ok = (Cout % 8 == 0) && (!residual || ((uintptr_t)residual & 15) == 0);
 
   CUtensorMap ta, ta2, tb;

@@ -15,6 +15,8 @@
 // * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
 // * Persistent: grid = min(#tiles, #SMs), static round-robin tile schedule (n fastest).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -57,6 +59,7 @@ struct GemmParams {
   long long ld_res, res_batch_stride;
   int act;
   float alpha;                 // scale applied to the accumulator before bias
+  int debug;                   // perf experiments: 1 = no epilogue stores, 2 = no A loads, 4 = no B loads, 8 = no MMAs, 16 = empty epilogue
 };
 
 template <int BLOCK_N>
@@ -65,9 +68,12 @@ struct GemmSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kBarrierBytes;
+  static constexpr int kStagingBytes = 4 * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose tile
+  static constexpr int kRowMetaBytes = 4 * 640;           // per-warp: out offsets, residual offsets, row bias
+  static constexpr int kEpiBytes = kStagingBytes + kRowMetaBytes;
+  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kBarrierBytes - kEpiBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
-  static constexpr int kTotalBytes = kStages * kStageBytes + kBarrierBytes + 1024;
+  static constexpr int kTotalBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;
 };
 
 template <typename OutT>
@@ -107,7 +113,7 @@ __device__ __forceinline__ void load_chunk8<__half>(const __half* src, float* v)
   }
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
@@ -118,12 +124,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using S = GemmSmem<BLOCK_N>;
   constexpr int kStages = S::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array itself, so
+  // the compiler keeps the shared address space (LDS/STS, no aliasing with global stores)
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint8_t* stage_smem = smem + kStages * S::kStageBytes;
+  uint8_t* rowmeta_smem = stage_smem + S::kStagingBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -177,10 +186,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], a_bytes + (uint32_t)S::kBBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], ((p.debug & 2) ? 0u : a_bytes) + ((p.debug & 4) ? 0u : (uint32_t)S::kBBytes));
           void* sa = smem_a + stage * S::kABytes;
           void* sb = smem_b + stage * S::kBBytes;
-          if (p.conv) {
+          if (p.debug & 2) {
+          } else if (p.conv) {
             if (kb < tap_blocks) {
               const int tap = kb / p.cin_blocks;
               const int cb = kb - tap * p.cin_blocks;
@@ -194,8 +204,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_3d(&tmA, &full_bar[stage], sa, kb * kBlockK, m_blk * kBlockM, p.a_batched ? b : 0,
                         kEvictNormal);
           }
-          tma_load_3d(&tmB, &full_bar[stage], sb, kb * kBlockK, n_blk * BLOCK_N, p.b_batched ? b : 0,
-                      kEvictLast);
+          if (!(p.debug & 4))
+            tma_load_3d(&tmB, &full_bar[stage], sb, kb * kBlockK, n_blk * BLOCK_N, p.b_batched ? b : 0,
+                        kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -203,48 +214,59 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
     constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kAccStrideCols;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    if (lane == 0) {            // a single thread runs the whole issue loop (no warp-wide polling / syncs)
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = make_desc_sw128(smem_u32(smem_a + stage * S::kABytes), 16, 1024);
-          const uint64_t bdesc = make_desc_sw128(smem_u32(smem_b + stage * S::kBBytes), 16, 1024);
+        const uint32_t d_tmem = tmem_base + acc * kAccStrideCols;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_desc_sw128(a_base + stage * S::kABytes, 16, 1024);
+          const uint64_t bdesc = make_desc_sw128(b_base + stage * S::kBBytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 32 bytes (16 fp16) along K inside the 128B swizzle row: +2 in 16-byte units
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (!(p.debug & 8)) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);           // smem slot reusable once these MMAs retire
           if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ======================================================================= epilogue (4 warps)
+    // TMEM gives each thread one accumulator ROW (32 consecutive columns per tcgen05.ld).  Writing that
+    // straight to global memory touches 32 different 128-byte lines per store instruction, so every
+    // 32x32 chunk is transposed through a padded smem tile first: afterwards lane = column, and each
+    // residual load / output store of a row segment is one fully coalesced 128-byte (fp32) access.
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
+    float (*stg)[33] = reinterpret_cast<float (*)[33]>(stage_smem + quad * (32 * 33 * 4));
+    // per-warp row tables (16-byte aligned): element offsets of each of the warp's 32 rows relative to the
+    // batch base (0xFFFFFFFF = row outside the tensor), same for the residual, and the per-row bias
+    uint32_t* s_off_out = reinterpret_cast<uint32_t*>(rowmeta_smem + quad * 640);
+    uint32_t* s_off_res = s_off_out + 32;
+    float* s_bias_r = reinterpret_cast<float*>(s_off_res + 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    OutT* out = reinterpret_cast<OutT*>(p.out);
-    const OutT* res = reinterpret_cast<const OutT*>(p.residual);
+    OutT* __restrict__ out = reinterpret_cast<OutT*>(p.out);
+    const OutT* __restrict__ res = reinterpret_cast<const OutT*>(p.residual);
+    const float* __restrict__ bias = p.bias;
     constexpr int kOutCols = BLOCK_N;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles;
       int rest = tile / p.n_tiles;
       const int m_blk = rest % p.m_tiles;
       const int b = rest / p.m_tiles;
-      // ---- row -> output address
+      // ---- this thread's row -> output offsets (published to the warp through smem)
       bool row_ok;
       long long orow;   // linear output row index (pixel index for conv)
       long long opix = 0;
@@ -264,112 +286,128 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r = m_blk * kBlockM + row_in_tile;
         row_ok = r < p.M;
         orow = r;
-        if (p.rows_per_img) img = r / p.rows_per_img;
       }
-      OutT* orow_ptr = out + (long long)b * p.out_batch_stride + orow * p.ldo;
-      const OutT* rrow_ptr = res ? res + (long long)b * p.res_batch_stride + orow * p.ld_res : nullptr;
-      const float* rv = p.rowvec ? p.rowvec + (long long)img * p.ld_rowvec : nullptr;
-      const float bias_r = (p.bias && p.bias_row && row_ok) ? p.bias[orow] : 0.f;
+      const float* __restrict__ rv = p.rowvec ? p.rowvec + (long long)img * p.ld_rowvec : nullptr;
+      __syncwarp();
+      s_off_out[lane] = row_ok ? (uint32_t)(orow * p.ldo) : 0xFFFFFFFFu;
+      s_off_res[lane] = (uint32_t)(orow * p.ld_res);
+      s_bias_r[lane] = (bias && p.bias_row && row_ok) ? bias[orow] : 0.f;
+      __syncwarp();
+      OutT* __restrict__ out_b = out + (long long)b * p.out_batch_stride;
+      const OutT* __restrict__ res_b = res ? res + (long long)b * p.res_batch_stride : nullptr;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStrideCols + ((uint32_t)(quad * 32) << 16);
 
-      if (p.act == ACT_GEGLU) {
-        // tile columns [0,BN/2) = value, [BN/2,BN) = gate for the same output columns
-        constexpr int H = kOutCols / 2;
-        const int ncol0 = n_blk * H;
-        const int n_out = p.N / 2;
-#pragma unroll 1
-        for (int c = 0; c < H; c += 16) {
-          uint32_t rv_[16], rg_[16];
-          tmem_ld_32x16(t_row + c, rv_);
-          tmem_ld_32x16(t_row + H + c, rg_);
-          tmem_ld_wait();
-          if (row_ok) {
+      if (p.debug & 16) {
+      } else if (p.out_nchw) {
+        // tiny Cout (<= 8): thread = pixel, consecutive lanes = consecutive pixels -> already coalesced
+        uint32_t r[16];
+        tmem_ld_32x16(t_row, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          const long long plane = (long long)p.OH * p.OW;
 #pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-              const int col = ncol0 + c + j;
-              if (col < n_out) {
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float v = __uint_as_float(rv_[j + e]) + p.bias[n_blk * kOutCols + c + j + e];
-                  float g = __uint_as_float(rg_[j + e]) + p.bias[n_blk * kOutCols + H + c + j + e];
-                  o[e] = v * gelu_erf_f(g);
-                }
-                store_chunk8<OutT>(orow_ptr + col, o);
-              }
+          for (int e = 0; e < 8; ++e) {
+            if (e < p.N) {
+              float v = __uint_as_float(r[e]) * p.alpha;
+              if (bias) v += bias[e];
+              if (rv) v += rv[e];
+              if (p.act == ACT_SILU) v = silu_f(v);
+              out[((long long)img * p.N + e) * plane + opix] = (OutT)v;
             }
           }
         }
       } else {
-        const int ncol0 = n_blk * kOutCols;
-#pragma unroll 1
-        for (int c = 0; c < kOutCols; c += 32) {
-          uint32_t r[32];
-          if (kOutCols - c >= 32) {
-            tmem_ld_32x32(t_row + c, r);
-          } else {
-            uint32_t r16[16];
-            tmem_ld_32x16(t_row + c, r16);
+        const bool geglu = p.act == ACT_GEGLU;
+        const int width = geglu ? kOutCols / 2 : kOutCols;          // output columns this tile produces
+        const int ncol0 = n_blk * width;
+        const int n_out = geglu ? p.N / 2 : p.N;
+        // one 32-row x CW-column chunk (CW = 32, or 16 for the tail of an 80/16-wide GEGLU tile)
+        auto do_chunk = [&](int c, auto cw_tag) {
+          constexpr int CW = decltype(cw_tag)::value;
+          const int col = ncol0 + c + lane;
+          const bool col_ok = lane < CW && col < n_out;
+          // row offsets of this warp's 32 rows: 8 broadcast 16-byte loads
+          uint32_t roff[32];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) r[e] = r16[e];
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const uint4 t4 = reinterpret_cast<const uint4*>(s_off_out)[q4];
+            roff[4 * q4] = t4.x; roff[4 * q4 + 1] = t4.y; roff[4 * q4 + 2] = t4.z; roff[4 * q4 + 3] = t4.w;
           }
-          tmem_ld_wait();
-          if (row_ok) {
+          // residual rows for this chunk: 32 independent coalesced loads in flight per warp, issued
+          // before the TMEM load / transpose so their latency is hidden
+          float rres[32];
+          if (res_b != nullptr && !geglu) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const int col = ncol0 + c + j;
-              if (c + j < kOutCols && col < p.N) {
-                float o[8];
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const uint4 t4 = reinterpret_cast<const uint4*>(s_off_res)[q4];
+              const uint32_t o4[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[j + e]) * p.alpha;
-                if (p.bias) {
-                  if (p.bias_row) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] += bias_r;
-                  } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) if (col + e < p.N) o[e] += p.bias[col + e];
-                  }
-                }
-                if (rv) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) if (col + e < p.N) o[e] += rv[col + e];
-                }
-                if (p.out_nchw) {
-                  const long long plane = (long long)p.OH * p.OW;
-                  for (int e = 0; e < 8 && col + e < p.N; ++e) {
-                    float v = o[e];
-                    if (p.act == ACT_SILU) v = silu_f(v);
-                    out[((long long)img * p.N + col + e) * plane + opix] = (OutT)v;
-                  }
-                } else if (p.vec_ok && col + 8 <= p.N) {
-                  if (rrow_ptr) {
-                    float rr[8];
-                    load_chunk8<OutT>(rrow_ptr + col, rr);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] += rr[e];
-                  }
-                  if (p.act == ACT_SILU) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = silu_f(o[e]);
-                  }
-                  store_chunk8<OutT>(orow_ptr + col, o);
-                } else {
-                  // ragged tail (N not a multiple of 8): scalar path
-                  for (int e = 0; e < 8 && col + e < p.N; ++e) {
-                    float v = o[e];
-                    if (rrow_ptr) v += (float)rrow_ptr[col + e];
-                    if (p.act == ACT_SILU) v = silu_f(v);
-                    orow_ptr[col + e] = (OutT)v;
-                  }
-                }
+              for (int e = 0; e < 4; ++e) {
+                const int rr = 4 * q4 + e;
+                rres[rr] = (col_ok && roff[rr] != 0xFFFFFFFFu) ? (float)res_b[(size_t)o4[e] + col] : 0.f;
               }
             }
           }
-        }
+          uint32_t r[CW];
+          if constexpr (CW == 32) tmem_ld_32x32(t_row + c, r); else tmem_ld_32x16(t_row + c, r);
+          tmem_ld_wait();
+          if (geglu) {
+            // value half is in r; fetch the gate half and combine per row before the transpose
+            uint32_t g[CW];
+            if constexpr (CW == 32) tmem_ld_32x32(t_row + width + c, g); else tmem_ld_32x16(t_row + width + c, g);
+            tmem_ld_wait();
+            const float* __restrict__ bv = bias + n_blk * kOutCols + c;
+            const float* __restrict__ bg = bv + width;
+#pragma unroll
+            for (int e = 0; e < CW; ++e) {
+              const float v = __uint_as_float(r[e]) + bv[e];
+              const float gg = __uint_as_float(g[e]) + bg[e];
+              r[e] = __float_as_uint(v * gelu_erf_f(gg));
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < CW; ++e) stg[lane][e] = __uint_as_float(r[e]);
+          __syncwarp();
+          // ---- transposed phase: lane = column; all smem reads first, then branch-free math + predicated stores
+          float vals[32];
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr][lane];
+          if (!geglu) {
+            float add = 0.f;
+            if (col_ok) {
+              if (bias && !p.bias_row) add += bias[col];
+              if (rv) add += rv[col];
+            }
+            if (p.bias_row) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) vals[rr] = fmaf(vals[rr], p.alpha, add + s_bias_r[rr]);
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) vals[rr] = fmaf(vals[rr], p.alpha, add);
+            }
+            if (res_b != nullptr) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) vals[rr] += rres[rr];
+            }
+            if (p.act == ACT_SILU) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) vals[rr] = silu_f(vals[rr]);
+            }
+          }
+          if (!(p.debug & 1)) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (col_ok && roff[rr] != 0xFFFFFFFFu) out_b[(size_t)roff[rr] + col] = (OutT)vals[rr];
+          }
+          __syncwarp();
+        };
+        int c = 0;
+#pragma unroll 1
+        for (; c + 32 <= width; c += 32) do_chunk(c, std::integral_constant<int, 32>{});
+        if (c < width) do_chunk(c, std::integral_constant<int, 16>{});
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();

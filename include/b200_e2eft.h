@@ -139,6 +139,9 @@ int b200_nhwc_to_nchw_f32(const void* x, int in_f32, int NB, int C, long long HW
 
 /* debugging: force a BLOCK_N (0 = automatic) */
 void b200_debug_force_block_n(int bn);
+/* debugging / perf experiments (results are wrong when set): 1 = skip epilogue stores, 2 = skip A loads,
+ * 4 = skip W loads */
+void b200_debug_set_flags(int flags);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,11 @@ import torch
 from diffusion_e2e_ft_b200 import ops
 what = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+from diffusion_e2e_ft_b200 import lib as _l
+if len(sys.argv) > 3:
+    _l.load().b200_debug_set_flags(int(sys.argv[3]))
+if len(sys.argv) > 4:
+    _l.load().b200_debug_force_block_n(int(sys.argv[4]))
 dev = "cuda"
 g = torch.Generator(device="cpu").manual_seed(0)
 r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).half().to(dev)
