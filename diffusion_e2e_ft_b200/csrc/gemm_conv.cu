@@ -81,12 +81,12 @@ int sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------
-template <int BN, typename OutT>
+template <int BN, typename OutT, bool SWAP>
 static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
                       const GemmParams& p, cudaStream_t st) {
   using S = GemmSmem<BN>;
   static bool configured = false;
-  auto kern = gemm_conv_kernel<BN, OutT>;
+  auto kern = gemm_conv_kernel<BN, OutT, SWAP>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes);
     if (e != cudaSuccess) {
@@ -103,42 +103,38 @@ static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtenso
 }
 
 template <typename OutT>
-static int launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
+static int launch_bn(int bn, bool swap, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
                      const GemmParams& p, cudaStream_t st) {
-  switch (bn) {
-    case 32: return launch_one<32, OutT>(a, a2, b, p, st);
-    case 64: return launch_one<64, OutT>(a, a2, b, p, st);
-    case 128: return launch_one<128, OutT>(a, a2, b, p, st);
-    case 160: return launch_one<160, OutT>(a, a2, b, p, st);
-    case 256: return launch_one<256, OutT>(a, a2, b, p, st);
+  if (swap) {
+    switch (bn) {
+      case 64: return launch_one<64, OutT, true>(a, a2, b, p, st);
+      case 128: return launch_one<128, OutT, true>(a, a2, b, p, st);
+      case 256: return launch_one<256, OutT, true>(a, a2, b, p, st);
+    }
+  } else {
+    switch (bn) {
+      case 32: return launch_one<32, OutT, false>(a, a2, b, p, st);
+      case 64: return launch_one<64, OutT, false>(a, a2, b, p, st);
+      case 128: return launch_one<128, OutT, false>(a, a2, b, p, st);
+      case 160: return launch_one<160, OutT, false>(a, a2, b, p, st);
+      case 256: return launch_one<256, OutT, false>(a, a2, b, p, st);
+    }
   }
-  set_last_error("unsupported BLOCK_N %d", bn);
+  set_last_error("unsupported tile width %d (swap=%d)", bn, (int)swap);
   return -1;
 }
 
-// Pick BLOCK_N: minimise (waves x per-tile cost).  Per-tile cost ~ BLOCK_N MMA columns + fixed
-// epilogue/prologue overhead.  GEGLU needs value|gate halves, any of the sizes works (even).
-static int pick_block_n(int N, long long m_tiles_total, int force) {
-  if (force) return force;
-  const int cands[5] = {256, 160, 128, 64, 32};
-  int best = 32;
-  double best_cost = 1e30;
-  for (int i = 0; i < 5; ++i) {
-    int bn = cands[i];
-    long long n_tiles = (N + bn - 1) / bn;
-    long long tiles = n_tiles * m_tiles_total;
-    long long waves = (tiles + sm_count() - 1) / sm_count();
-    double cost = (double)waves * (bn + 24.0);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = bn;
-    }
-  }
-  return best;
+// Per-k-block time of a 128 x n MMA tile in SM cycles: 2n tensor cycles (K=64), floored by the measured
+// ~365-cycle producer/issuer barrier round trip (profiles/README_r01.md).
+static double kblock_cycles(int n) { return n * 2.0 > 365.0 ? n * 2.0 : 365.0; }
+static double tiles_cost(long long tiles, int n) {
+  long long waves = (tiles + sm_count() - 1) / sm_count();
+  return (double)waves * (kblock_cycles(n) + 40.0);
 }
 
 static int g_force_bn = 0;
 static int g_debug = 0;
+static int g_swap_mode = 1;   // 1 = automatic (swap operands when Cout % 128 == 0), 0 = never
 
 }  // namespace b200
 
@@ -147,6 +143,7 @@ using namespace b200;
 extern "C" const char* b200_last_error_string(void) { return b200::last_error(); }
 extern "C" void b200_debug_force_block_n(int bn) { b200::g_force_bn = bn; }
 extern "C" void b200_debug_set_flags(int f) { b200::g_debug = f; }
+extern "C" void b200_debug_set_swap(int m) { b200::g_swap_mode = m; }
 extern "C" int b200_abi_version(void) { return 1; }
 // Tile width used by the GEGLU epilogue for a packed width N (= 2 x output width); weights must be
 // packed per tile as [value half | gate half] with this width.
@@ -180,55 +177,82 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.m_tiles = (M + kBlockM - 1) / kBlockM;
   p.a_batched = (a_batch_stride != 0 && batch > 1);
   p.b_batched = (w_batch_stride != 0 && batch > 1);
-  int bn = pick_block_n(N, (long long)p.m_tiles * batch, g_force_bn);
-  if (act == ACT_GEGLU) bn = b200_geglu_block_n(N);
-  B200_CHECK_ARG(bn != 0, "b200_linear: GEGLU N=%d not tileable", N);
-  p.n_tiles = (N + bn - 1) / bn;
+  // tile shape: normal (rows = 128 pixels, bn channels) vs swapped (rows = 128 channels, bn pixels)
+  const bool can_swap = g_swap_mode && (N % 128 == 0) && act != ACT_GEGLU && !bias_row && batch == 1;
+  bool swap = false;
+  int bn = 0;
+  double best = 1e30;
+  if (act == ACT_GEGLU) {
+    bn = b200_geglu_block_n(N);
+    B200_CHECK_ARG(bn != 0, "b200_linear: GEGLU N=%d not tileable", N);
+  } else {
+    const int nc[5] = {256, 160, 128, 64, 32};
+    for (int i = 0; i < 5; ++i) {
+      if (g_force_bn && nc[i] != g_force_bn) continue;
+      double c = tiles_cost((long long)p.m_tiles * batch * ((N + nc[i] - 1) / nc[i]), nc[i]);
+      if (c < best - 1e-9) { best = c; bn = nc[i]; swap = false; }
+    }
+    if (can_swap) {
+      const int pc[3] = {256, 128, 64};
+      for (int i = 0; i < 3; ++i) {
+        if (g_force_bn && pc[i] != g_force_bn) continue;
+        double c = tiles_cost((long long)((M + pc[i] - 1) / pc[i]) * (N / 128), pc[i]) * 0.95;  // cheaper epilogue
+        if (c < best - 1e-9) { best = c; bn = pc[i]; swap = true; }
+      }
+    }
+    B200_CHECK_ARG(bn != 0, "b200_linear: no tile shape for N=%d (forced %d)", N, g_force_bn);
+  }
+  if (swap) {
+    p.m_tiles = (M + bn - 1) / bn;
+    p.n_tiles = N / 128;
+  } else {
+    p.n_tiles = (N + bn - 1) / bn;
+  }
   p.out = out; p.ldo = ldo; p.out_batch_stride = out_batch_stride; p.out_f32 = out_f32;
   p.bias = bias; p.bias_row = bias_row;
   p.residual = residual; p.ld_res = ld_res; p.res_batch_stride = res_batch_stride;
   p.act = act; p.alpha = alpha; p.debug = g_debug;
   p.out_mul = 1;
-  p.vec_ok = (ldo % 8 == 0) && (out_batch_stride % 8 == 0) &&
-             (!residual || (ld_res % 8 == 0 && res_batch_stride % 8 == 0 && ((uintptr_t)residual & 15) == 0));
+  p.vec_ok = 0;
 
   CUtensorMap ta, tb;
   {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(p.a_batched ? batch : 1)};
     uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(p.a_batched ? a_batch_stride : (long long)M * lda) * 2};
-    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    uint32_t box[3] = {kBlockK, (uint32_t)(swap ? bn : kBlockM), 1};
     int r = encode_tmap(&ta, A, 3, dims, str, box, nullptr);
     if (r) return r;
   }
   {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)(p.b_batched ? batch : 1)};
     uint64_t str[2] = {(uint64_t)ldw * 2, (uint64_t)(p.b_batched ? w_batch_stride : (long long)N * ldw) * 2};
-    uint32_t box[3] = {kBlockK, (uint32_t)bn, 1};
+    uint32_t box[3] = {kBlockK, (uint32_t)(swap ? kBlockM : bn), 1};
     int r = encode_tmap(&tb, W, 3, dims, str, box, nullptr);
     if (r) return r;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  return out_f32 ? launch_bn<float>(bn, ta, ta, tb, p, st) : launch_bn<__half>(bn, ta, ta, tb, p, st);
+  return out_f32 ? launch_bn<float>(bn, swap, ta, ta, tb, p, st) : launch_bn<__half>(bn, swap, ta, ta, tb, p, st);
 }
 
 // Choose the (bw, bh) output-pixel patch of an M tile: bw*bh <= 128, maximise useful rows.
-static void pick_patch(int Ho, int Wo, int stride, int* bw_out, int* bh_out) {
+static double pick_patch(int Ho, int Wo, int stride, int target, int* bw_out, int* bh_out) {
   double best = -1;
   int bbw = 1, bbh = 1;
-  for (int bw = 1; bw <= 128 && bw <= Wo; ++bw) {
+  for (int bw = 1; bw <= target && bw <= Wo; ++bw) {
     if (bw * stride > 256) break;
-    int bh = 128 / bw;
+    int bh = target / bw;
     if (bh > Ho) bh = Ho;
     if (bh * stride > 256) bh = 256 / stride;
     if (bh < 1) continue;
     long long tw = (Wo + bw - 1) / bw, th = (Ho + bh - 1) / bh;
-    double eff = (double)Ho * Wo / (double)(tw * th * 128);
+    double eff = (double)Ho * Wo / (double)(tw * th * target);
     // prefer wider rows on ties (longer contiguous TMA rows / stores)
     if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > bbw)) {
       best = eff; bbw = bw; bbh = bh;
     }
   }
   *bw_out = bbw; *bh_out = bbh;
+  return best;
 }
 
 extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, const void* X2, int C2,
@@ -256,7 +280,34 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   p.N = Cout;
   p.batch = 1;
   p.Ho = Ho; p.Wo = Wo;
-  pick_patch(Ho, Wo, stride, &p.bw, &p.bh);
+  const bool can_swap = g_swap_mode && (Cout % 128 == 0) && !out_nchw;
+  bool swap = false;
+  int pix = 128, bn_norm = 0;
+  {
+    double best = 1e30;
+    int bw, bh;
+    pick_patch(Ho, Wo, stride, 128, &bw, &bh);
+    const long long mt = (long long)NB * ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh);
+    const int nc[5] = {256, 160, 128, 64, 32};
+    for (int i = 0; i < 5; ++i) {
+      if (g_force_bn && nc[i] != g_force_bn) continue;
+      double c = tiles_cost(mt * ((Cout + nc[i] - 1) / nc[i]), nc[i]);
+      if (c < best - 1e-9) { best = c; bn_norm = nc[i]; swap = false; }
+    }
+    if (can_swap) {
+      const int pc[3] = {256, 128, 64};
+      for (int i = 0; i < 3; ++i) {
+        if (g_force_bn && pc[i] != g_force_bn) continue;
+        pick_patch(Ho, Wo, stride, pc[i], &bw, &bh);
+        long long tiles = (long long)NB * ((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * (Cout / 128);
+        double c = tiles_cost(tiles, pc[i]) * 0.95;
+        if (c < best - 1e-9) { best = c; pix = pc[i]; swap = true; }
+      }
+    }
+    if (!swap) pix = 128;
+    B200_CHECK_ARG(swap || bn_norm != 0, "b200_conv2d_nhwc: no tile shape (forced %d)", g_force_bn);
+  }
+  pick_patch(Ho, Wo, stride, pix, &p.bw, &p.bh);
   p.tiles_w = (Wo + p.bw - 1) / p.bw;
   p.tiles_h = (Ho + p.bh - 1) / p.bh;
   p.m_tiles = NB * p.tiles_w * p.tiles_h;
@@ -269,8 +320,14 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   p.num_k_blocks = num_taps * p.cin_blocks + p.k2_blocks;
   p.out_mul = out_mul; p.out_oy = out_oy; p.out_ox = out_ox;
   p.OH = Ho * out_mul; p.OW = Wo * out_mul;
-  int bn = pick_block_n(Cout, p.m_tiles, g_force_bn);
-  p.n_tiles = (Cout + bn - 1) / bn;
+  int bn;
+  if (swap) {
+    bn = pix;
+    p.n_tiles = Cout / 128;
+  } else {
+    bn = bn_norm;
+    p.n_tiles = (Cout + bn - 1) / bn;
+  }
   p.out = out; p.ldo = Cout; p.out_f32 = out_f32; p.out_nchw = out_nchw;
   p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec;
   p.residual = residual; p.ld_res = Cout;
@@ -298,10 +355,10 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
     const long long Kt = (long long)num_taps * Cin + (X2 ? C2 : 0);
     uint64_t dims[3] = {(uint64_t)Kt, (uint64_t)Cout, 1};
     uint64_t str[2] = {(uint64_t)Kt * 2, (uint64_t)Kt * Cout * 2};
-    uint32_t box[3] = {kBlockK, (uint32_t)bn, 1};
+    uint32_t box[3] = {kBlockK, (uint32_t)(swap ? kBlockM : bn), 1};
     int r = encode_tmap(&tb, Wp, 3, dims, str, box, nullptr);
     if (r) return r;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  return out_f32 ? launch_bn<float>(bn, ta, ta2, tb, p, st) : launch_bn<__half>(bn, ta, ta2, tb, p, st);
+  return out_f32 ? launch_bn<float>(bn, swap, ta, ta2, tb, p, st) : launch_bn<__half>(bn, swap, ta, ta2, tb, p, st);
 }

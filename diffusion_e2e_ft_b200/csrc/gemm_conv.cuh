@@ -118,7 +118,13 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
-template <int BLOCK_N, typename OutT>
+// SWAP = false: accumulator rows (TMEM lanes) = 128 pixels, columns = BLOCK_N output channels.
+// SWAP = true : operands swapped — rows = 128 output channels (weights are the M operand), columns =
+//               BLOCK_N pixels (activations are the N operand).  Used when Cout % 128 == 0: a 128-channel
+//               layer then issues 128x256 MMAs (half the operand smem traffic and half the per-k-block
+//               barrier round trips of 128x128), and since lanes = channels the NHWC stores of one
+//               accumulator column are contiguous — no smem transpose in the epilogue.
+template <int BLOCK_N, typename OutT, bool SWAP>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -142,7 +148,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
-  const uint32_t a_bytes = p.conv ? (uint32_t)(p.bw * p.bh * kBlockK * 2) : (uint32_t)S::kABytes;
+  // bytes each stage receives: the activation box of a conv tile may hold fewer pixels than the tile
+  const uint32_t act_bytes = p.conv ? (uint32_t)(p.bw * p.bh * kBlockK * 2)
+                                    : (uint32_t)((SWAP ? BLOCK_N : kBlockM) * kBlockK * 2);
+  const uint32_t w_bytes = (uint32_t)((SWAP ? kBlockM : BLOCK_N) * kBlockK * 2);
+  const uint32_t a_bytes = SWAP ? w_bytes : act_bytes;
+  const uint32_t b_bytes = SWAP ? act_bytes : w_bytes;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -186,26 +197,31 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], ((p.debug & 2) ? 0u : a_bytes) + ((p.debug & 4) ? 0u : (uint32_t)S::kBBytes));
+          mbar_arrive_expect_tx(&full_bar[stage], ((p.debug & 2) ? 0u : a_bytes) + ((p.debug & 4) ? 0u : b_bytes));
           void* sa = smem_a + stage * S::kABytes;
           void* sb = smem_b + stage * S::kBBytes;
-          if (p.debug & 2) {
-          } else if (p.conv) {
-            if (kb < tap_blocks) {
-              const int tap = kb / p.cin_blocks;
-              const int cb = kb - tap * p.cin_blocks;
-              tma_load_4d(&tmA, &full_bar[stage], sa, cb * kBlockK, w0 * p.in_stride + p.tap_dx[tap],
-                          h0 * p.in_stride + p.tap_dy[tap], img, kEvictNormal);
+          void* s_act = SWAP ? sb : sa;            // activations: M operand normally, N operand when swapped
+          void* s_w = SWAP ? sa : sb;
+          constexpr int kActRows = SWAP ? BLOCK_N : kBlockM;
+          constexpr int kWRows = SWAP ? kBlockM : BLOCK_N;
+          if (!(p.debug & 2)) {
+            if (p.conv) {
+              if (kb < tap_blocks) {
+                const int tap = kb / p.cin_blocks;
+                const int cb = kb - tap * p.cin_blocks;
+                tma_load_4d(&tmA, &full_bar[stage], s_act, cb * kBlockK, w0 * p.in_stride + p.tap_dx[tap],
+                            h0 * p.in_stride + p.tap_dy[tap], img, kEvictNormal);
+              } else {
+                tma_load_4d(&tmA2, &full_bar[stage], s_act, (kb - tap_blocks) * kBlockK, w0, h0, img,
+                            kEvictNormal);
+              }
             } else {
-              tma_load_4d(&tmA2, &full_bar[stage], sa, (kb - tap_blocks) * kBlockK, w0, h0, img,
+              tma_load_3d(&tmA, &full_bar[stage], s_act, kb * kBlockK, m_blk * kActRows, p.a_batched ? b : 0,
                           kEvictNormal);
             }
-          } else {
-            tma_load_3d(&tmA, &full_bar[stage], sa, kb * kBlockK, m_blk * kBlockM, p.a_batched ? b : 0,
-                        kEvictNormal);
           }
           if (!(p.debug & 4))
-            tma_load_3d(&tmB, &full_bar[stage], sb, kb * kBlockK, n_blk * BLOCK_N, p.b_batched ? b : 0,
+            tma_load_3d(&tmB, &full_bar[stage], s_w, kb * kBlockK, n_blk * kWRows, p.b_batched ? b : 0,
                         kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -249,6 +265,109 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // residual load / output store of a row segment is one fully coalesced 128-byte (fp32) access.
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
+    if constexpr (SWAP) {
+      // ------------------------------------------------------------------ swapped: lane = channel
+      OutT* __restrict__ out = reinterpret_cast<OutT*>(p.out);
+      const OutT* __restrict__ res = reinterpret_cast<const OutT*>(p.residual);
+      const float* __restrict__ bias = p.bias;
+      uint32_t* tab = reinterpret_cast<uint32_t*>(stage_smem);     // [2 acc][out|res][BLOCK_N] pixel offsets
+      const int et = threadIdx.x - 64;                             // 0..127 within the epilogue warps
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;                        // channel tile
+        int rest = tile / p.n_tiles;
+        const int m_blk = rest % p.m_tiles;                        // pixel tile
+        const int b = rest / p.m_tiles;
+        int img = 0, th = 0, tw = 0;
+        if (p.conv) {
+          tw = m_blk % p.tiles_w;
+          const int r2 = m_blk / p.tiles_w;
+          th = r2 % p.tiles_h;
+          img = r2 / p.tiles_h;
+        }
+        uint32_t* t_out = tab + acc * (2 * BLOCK_N);
+        uint32_t* t_res = t_out + BLOCK_N;
+        for (int pi = et; pi < BLOCK_N; pi += 128) {
+          bool ok;
+          long long orow;
+          if (p.conv) {
+            const int dh = pi / p.bw;
+            const int dw = pi - dh * p.bw;
+            const int ho = th * p.bh + dh, wo = tw * p.bw + dw;
+            ok = (dh < p.bh) && (ho < p.Ho) && (wo < p.Wo);
+            orow = ((long long)img * p.OH + (ho * p.out_mul + p.out_oy)) * p.OW + (wo * p.out_mul + p.out_ox);
+          } else {
+            const long long r = (long long)m_blk * BLOCK_N + pi;
+            ok = r < p.M;
+            orow = r;
+          }
+          t_out[pi] = ok ? (uint32_t)(orow * p.ldo) : 0xFFFFFFFFu;
+          t_res[pi] = (uint32_t)(orow * p.ld_res);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");             // table visible to the 4 epilogue warps
+        const int ch = n_blk * kBlockM + row_in_tile;
+        const bool ch_ok = ch < p.N;
+        float add = 0.f;
+        if (ch_ok) {
+          if (bias) add += bias[ch];
+          if (p.rowvec) add += p.rowvec[(long long)img * p.ld_rowvec + ch];
+        }
+        OutT* __restrict__ out_b = out + (long long)b * p.out_batch_stride + ch;
+        const OutT* __restrict__ res_b = res ? res + (long long)b * p.res_batch_stride + ch : nullptr;
+
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * kAccStrideCols + ((uint32_t)(quad * 32) << 16);
+        if (!(p.debug & 16)) {
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t roff[32];
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const uint4 t4 = reinterpret_cast<const uint4*>(t_out + c)[q4];
+              roff[4 * q4] = t4.x; roff[4 * q4 + 1] = t4.y; roff[4 * q4 + 2] = t4.z; roff[4 * q4 + 3] = t4.w;
+            }
+            float rres[32];
+            if (res_b != nullptr) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const uint4 t4 = reinterpret_cast<const uint4*>(t_res + c)[q4];
+                const uint32_t o4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = 4 * q4 + e;
+                  rres[j] = (ch_ok && roff[j] != 0xFFFFFFFFu) ? (float)res_b[(size_t)o4[e]] : 0.f;
+                }
+              }
+            }
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + c, r);
+            tmem_ld_wait();
+            float vals[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vals[j] = fmaf(__uint_as_float(r[j]), p.alpha, add);
+            if (res_b != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) vals[j] += rres[j];
+            }
+            if (p.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) vals[j] = silu_f(vals[j]);
+            }
+            if (!(p.debug & 1)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (ch_ok && roff[j] != 0xFFFFFFFFu) out_b[(size_t)roff[j]] = (OutT)vals[j];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
     float (*stg)[33] = reinterpret_cast<float (*)[33]>(stage_smem + quad * (32 * 33 * 4));
     // per-warp row tables (16-byte aligned): element offsets of each of the warp's 32 rows relative to the
     // batch base (0xFFFFFFFF = row outside the tensor), same for the residual, and the per-row bias
@@ -415,6 +534,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+    }  // !SWAP
   }
 
   tc_fence_before();

@@ -142,6 +142,8 @@ void b200_debug_force_block_n(int bn);
 /* debugging / perf experiments (results are wrong when set): 1 = skip epilogue stores, 2 = skip A loads,
  * 4 = skip W loads */
 void b200_debug_set_flags(int flags);
+/* 1 (default) = swap operands automatically when Cout % 128 == 0; 0 = never */
+void b200_debug_set_swap(int mode);
 
 #ifdef __cplusplus
 }

@@ -228,6 +228,19 @@ def check_pointwise_and_post():
     return max(e1, e2, e3, e4), 1e-5
 
 
+def _noswap(fn):
+    """run a check with the swapped-operand mode disabled (exercises the transposed-epilogue path)."""
+    def run():
+        from diffusion_e2e_ft_b200 import lib
+        L = lib.load()
+        L.b200_debug_set_swap(0)
+        try:
+            return fn()
+        finally:
+            L.b200_debug_set_swap(1)
+    return run
+
+
 CHECKS = {
     "linear_basic": lambda: check_linear(),
     "linear_small_m": lambda: check_linear(M=8, N=1280, K=320),
@@ -252,6 +265,17 @@ CHECKS = {
     "conv_out_nchw": lambda: check_conv(Cin=128, Cout=3, out_f32=True, out_nchw=True, H=40, W=56),
     "conv_out4_nchw": lambda: check_conv(Cin=64, Cout=4, out_f32=True, out_nchw=True),
     "conv_in_im2col": check_conv_in,
+    "conv_swap_128_res_temb_f32": lambda: check_conv(H=40, W=40, Cin=128, Cout=128, rowvec=True, residual=True, out_f32=True),
+    "conv_swap_256_shortcut": lambda: check_conv(H=24, W=24, Cin=128, Cout=256, shortcut=128),
+    "conv_swap_s2": lambda: check_conv(H=32, W=32, Cin=64, Cout=128, stride=2),
+    "conv_swap_s2_vae": lambda: check_conv(H=32, W=48, Cin=128, Cout=128, stride=2, pad_mode="vae_down"),
+    "conv_swap_odd": lambda: check_conv(NB=1, H=15, W=20, Cin=64, Cout=128, residual=True),
+    "conv_swap_768": lambda: check_conv(NB=1, H=96, W=768, Cin=128, Cout=128, seed=9),
+    "conv_swap_1280_12": lambda: check_conv(NB=2, H=12, W=12, Cin=256, Cout=1280),
+    "conv_noswap_256": _noswap(lambda: check_conv(H=24, W=24, Cin=128, Cout=256, residual=True, out_f32=True)),
+    "linear_noswap_1280": _noswap(lambda: check_linear(M=2000, N=1280, K=1280, residual=True, seed=2)),
+    "linear_swap_small_m": lambda: check_linear(M=8, N=1280, K=1280, act=ops.ACT_SILU),
+    "linear_swap_ragged": lambda: check_linear(M=777, N=384, K=200, residual=True, out_f32=True),
     "gn_f16": lambda: check_group_norm(),
     "gn_f32_concat": lambda: check_group_norm(C1=1280, C2=640, in_f32=True),
     "gn_concat_f16_nosilu": lambda: check_group_norm(C1=640, C2=320, silu=False),
