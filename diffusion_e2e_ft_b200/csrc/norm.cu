@@ -93,25 +93,42 @@ __global__ void gn_stats_kernel(const T* __restrict__ x1, int C1, const T* __res
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x1, int C1, const T* __restrict__ x2, int C2,
                                 int HW, int groups, int pix_per_cta, const double* __restrict__ sums,
+                                const float* __restrict__ cs1, const float* __restrict__ cs2,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 float eps, int silu, __half* __restrict__ y, __half* __restrict__ raw) {
-  extern __shared__ float sm[];   // scale[C], shift[C]
+  extern __shared__ float sm[];   // scale[C], shift[C], then group (mean, rstd)[groups][2]
   const int C = C1 + C2;
   const int V = C / 8;
   const int n = blockIdx.y;
   const int cg = C / groups;
   const double cnt = (double)HW * cg;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cg;
-    const double su = sums[((long long)n * groups + g) * 2 + 0];
-    const double sq = sums[((long long)n * groups + g) * 2 + 1];
+  float* gstat = sm + 2 * C;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double su, sq;
+    if (sums) {
+      su = sums[((long long)n * groups + g) * 2 + 0];
+      sq = sums[((long long)n * groups + g) * 2 + 1];
+    } else {
+      // per-channel sums written by the producing kernels' epilogues; a group may straddle the concat
+      su = 0.0; sq = 0.0;
+      for (int c = g * cg; c < (g + 1) * cg; ++c) {
+        const float* src = c < C1 ? cs1 + ((long long)n * C1 + c) * 2 : cs2 + ((long long)n * C2 + (c - C1)) * 2;
+        su += (double)src[0];
+        sq += (double)src[1];
+      }
+    }
     const double mean = su / cnt;
     double var = sq / cnt - mean * mean;
     if (var < 0) var = 0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float a = rstd * gamma[c];
+    gstat[2 * g] = (float)mean;
+    gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cg;
+    const float a = gstat[2 * g + 1] * gamma[c];
     sm[c] = a;
-    sm[C + c] = beta[c] - (float)mean * a;
+    sm[C + c] = beta[c] - gstat[2 * g] * a;
   }
   __syncthreads();
   const int rpb = blockDim.x / V;
@@ -309,15 +326,38 @@ extern "C" int b200_group_norm_apply(const void* x1, int C1, const void* x2, int
   const int T = gn_block(C);
   const int ppc = gn_chunks(NB, HW, T / (C / 8));
   dim3 grid((HW + ppc - 1) / ppc, NB);
-  const size_t smem = 2 * C * sizeof(float);
+  const size_t smem = (2 * C + 2 * groups) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (in_f32)
     gn_apply_kernel<float><<<grid, T, smem, st>>>((const float*)x1, C1, (const float*)x2, C2, HW, groups, ppc, sums,
-                                                  gamma, beta, eps, silu, (__half*)y, (__half*)raw_copy);
+                                                  nullptr, nullptr, gamma, beta, eps, silu, (__half*)y, (__half*)raw_copy);
   else
     gn_apply_kernel<__half><<<grid, T, smem, st>>>((const __half*)x1, C1, (const __half*)x2, C2, HW, groups, ppc, sums,
-                                                   gamma, beta, eps, silu, (__half*)y, (__half*)raw_copy);
+                                                   nullptr, nullptr, gamma, beta, eps, silu, (__half*)y, (__half*)raw_copy);
   B200_CHECK_LAUNCH("gn_apply_kernel");
+  return 0;
+}
+
+extern "C" int b200_group_norm_apply_cs(const void* x1, int C1, const float* cs1, const void* x2, int C2,
+                                        const float* cs2, int in_f32, int NB, int HW, int groups,
+                                        const float* gamma, const float* beta, float eps, int silu, void* y,
+                                        void* raw_copy, void* stream) {
+  int r = gn_common_check("b200_group_norm_apply_cs", x1, C1, x2, C2, NB, HW, groups);
+  if (r) return r;
+  B200_CHECK_ARG(cs1 && (C2 == 0 || cs2) && gamma && beta && y, "b200_group_norm_apply_cs: null pointer");
+  const int C = C1 + C2;
+  const int T = gn_block(C);
+  const int ppc = gn_chunks(NB, HW, T / (C / 8));
+  dim3 grid((HW + ppc - 1) / ppc, NB);
+  const size_t smem = (2 * C + 2 * groups) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_f32)
+    gn_apply_kernel<float><<<grid, T, smem, st>>>((const float*)x1, C1, (const float*)x2, C2, HW, groups, ppc, nullptr,
+                                                  cs1, cs2, gamma, beta, eps, silu, (__half*)y, (__half*)raw_copy);
+  else
+    gn_apply_kernel<__half><<<grid, T, smem, st>>>((const __half*)x1, C1, (const __half*)x2, C2, HW, groups, ppc, nullptr,
+                                                   cs1, cs2, gamma, beta, eps, silu, (__half*)y, (__half*)raw_copy);
+  B200_CHECK_LAUNCH("gn_apply_kernel(cs)");
   return 0;
 }
 

@@ -42,6 +42,26 @@ class Stats:
 
 
 STATS = Stats()
+STATS.time_all = False
+STATS.op_events = []           # (name, start, end) when time_all
+
+
+def _timed(name):
+    """Bracket an op with CUDA events when STATS.time_all (bench.py's per-op breakdown of an eager step)."""
+    def deco(fn):
+        def wrapper(*a, **k):
+            if not STATS.time_all:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            STATS.op_events.append((name, e0, e1))
+            return out
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
 
 
 def _ck(rc, what):
@@ -103,8 +123,18 @@ def pack_geglu(w, b):
 
 
 # ------------------------------------------------------------------------------ GEMM
+FUSE_GN_STATS = True     # GroupNorm statistics from the producing GEMM/conv epilogue (no gn_stats pass)
+
+
+def _new_stats(nb, c, device):
+    return torch.zeros((nb, c, 2), dtype=F32, device=device)
+
+
+@_timed("gemm_linear")
 def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE, alpha=1.0,
-           bias_row=False):
+           bias_row=False, stats_rows_per_img=0):
+    """`stats_rows_per_img` > 0: also accumulate per-(image, channel) sum / sum-of-squares of the output
+    (attached to the result as `._cs`) for a following GroupNorm."""
     """a: [M,K] or [B,M,K] fp16 (last dim contiguous); w: [N,K] or [B,N,K] fp16."""
     _need_cuda(a, w)
     assert a.dtype == F16 and w.dtype == F16 and a.stride(-1) == 1 and w.stride(-1) == 1
@@ -119,6 +149,10 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
     assert out.stride(-1) == 1
     if residual is not None:
         assert residual.dtype == out.dtype and residual.stride(-1) == 1
+    cs = None
+    if (FUSE_GN_STATS and stats_rows_per_img and not batched and stats_rows_per_img % 64 == 0
+            and M % stats_rows_per_img == 0 and (N >= 128 or stats_rows_per_img % 128 == 0)):
+        cs = _new_stats(M // stats_rows_per_img, n_out, a.device)
     rc = _lib.load().b200_linear(
         _p(a), a.stride(-2), a.stride(0) if a.dim() == 3 else 0,
         _p(w), w.stride(-2), (w.stride(0) if w.dim() == 3 else 0),
@@ -126,16 +160,21 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
         _p(residual), residual.stride(-2) if residual is not None else 0,
         (residual.stride(0) if (residual is not None and batched) else 0),
         _p(out), out.stride(-2), out.stride(0) if batched else 0, int(out.dtype == F32),
-        act, float(alpha), _stream())
+        act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _stream())
     _lib.check(rc, "b200_linear")
     STATS.add("linear", 2 * B * M * N * K)
+    if cs is not None:
+        out._cs = cs
     return out
 
 
 # ------------------------------------------------------------------------------ conv
+@_timed("gemm_conv")
 def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, rowvec=None,
            residual=None, out=None, out_dtype=F16, out_nchw=False, act=ACT_NONE,
-           out_mul=1, out_off=(0, 0)):
+           out_mul=1, out_off=(0, 0), stats=None):
+    """`stats`: True -> allocate, or an existing [NB,Cout,2] fp32 tensor to accumulate into; the per-channel
+    sums of the output are attached to the result as `._cs` for a following GroupNorm."""
     """x: NHWC fp16 [NB,H,W,Cin]; wp: packed fp16 [Cout, len(taps)*Cin (+C2)]."""
     _need_cuda(x, wp)
     assert x.dtype == F16 and x.is_contiguous() and wp.dtype == F16 and wp.is_contiguous()
@@ -151,6 +190,11 @@ def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, r
         out = torch.empty(shape, dtype=out_dtype, device=x.device)
     if residual is not None:
         assert residual.dtype == out.dtype and residual.is_contiguous() and residual.shape == out.shape
+    assert out.is_contiguous() and tuple(out.shape) == (
+        (NB, cout, Ho * out_mul, Wo * out_mul) if out_nchw else (NB, Ho * out_mul, Wo * out_mul, cout)), out.shape
+    cs = None
+    if stats is not None and stats is not False and FUSE_GN_STATS and not out_nchw:
+        cs = _new_stats(NB, cout, x.device) if stats is True else stats
     dy = (c_int * len(taps))(*[t[0] for t in taps])
     dx = (c_int * len(taps))(*[t[1] for t in taps])
     fl = 2 * NB * Ho * Wo * cout * (len(taps) * Cin + C2)
@@ -162,15 +206,18 @@ def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, r
         _p(x), NB, H, W, Cin, _p(x2), C2, _p(wp), cout, len(taps), dy, dx, stride, Ho, Wo,
         out_mul, out_off[0], out_off[1], _p(bias), _p(rowvec),
         rowvec.stride(0) if rowvec is not None else 0, _p(residual), _p(out),
-        int(out.dtype == F32), int(out_nchw), act, _stream())
+        int(out.dtype == F32), int(out_nchw), act, _p(cs), _stream())
     _lib.check(rc, "b200_conv2d_nhwc")
     if ev is not None:
         ev[1].record()
         STATS.events.append((ev[0], ev[1], fl, (NB, H, W, Cin, C2, cout, len(taps), stride, str(out.dtype)[6:])))
     STATS.add("conv", fl)
+    if cs is not None:
+        out._cs = cs
     return out
 
 
+@_timed("im2col")
 def im2col3x3(x_nchw, kpad):
     _need_cuda(x_nchw)
     assert x_nchw.is_contiguous() and x_nchw.dtype in (F16, F32)
@@ -182,6 +229,7 @@ def im2col3x3(x_nchw, kpad):
 
 
 # ------------------------------------------------------------------------------ norms
+@_timed("group_norm")
 def group_norm(x1, gamma, beta, eps, groups=32, silu=True, x2=None, want_raw=False):
     """NHWC (fp16 or fp32) -> normalised fp16 NHWC of the channel-concat [x1 | x2]."""
     _need_cuda(x1, x2)
@@ -190,18 +238,26 @@ def group_norm(x1, gamma, beta, eps, groups=32, silu=True, x2=None, want_raw=Fal
     C2 = x2.shape[3] if x2 is not None else 0
     C = C1 + C2
     f32 = int(x1.dtype == F32)
-    sums = torch.zeros((NB, groups, 2), dtype=torch.float64, device=x1.device)
     L = _lib.load()
-    _ck(L.b200_group_norm_stats(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _stream()),
-               "b200_group_norm_stats")
     y = torch.empty((NB, H, W, C), dtype=F16, device=x1.device)
     raw = torch.empty_like(y) if want_raw else None
-    _ck(L.b200_group_norm_apply(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _p(gamma),
+    cs1 = getattr(x1, "_cs", None)
+    cs2 = getattr(x2, "_cs", None) if x2 is not None else None
+    if FUSE_GN_STATS and cs1 is not None and (x2 is None or cs2 is not None):
+        _ck(L.b200_group_norm_apply_cs(_p(x1), C1, _p(cs1), _p(x2), C2, _p(cs2), f32, NB, H * W, groups, _p(gamma),
                                        _p(beta), float(eps), int(silu), _p(y), _p(raw), _stream()),
-               "b200_group_norm_apply")
+            "b200_group_norm_apply_cs")
+        return (y, raw) if want_raw else y
+    sums = torch.zeros((NB, groups, 2), dtype=torch.float64, device=x1.device)
+    _ck(L.b200_group_norm_stats(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _stream()),
+        "b200_group_norm_stats")
+    _ck(L.b200_group_norm_apply(_p(x1), C1, _p(x2), C2, f32, NB, H * W, groups, _p(sums), _p(gamma),
+                                _p(beta), float(eps), int(silu), _p(y), _p(raw), _stream()),
+        "b200_group_norm_apply")
     return (y, raw) if want_raw else y
 
 
+@_timed("layer_norm")
 def layer_norm(x, gamma, beta, eps=1e-5):
     _need_cuda(x)
     assert x.is_contiguous()
@@ -214,6 +270,7 @@ def layer_norm(x, gamma, beta, eps=1e-5):
 
 
 # ------------------------------------------------------------------------------ attention
+@_timed("attention")
 def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None):
     """q: [B,Lq,>=heads*64] view, k/v: [B,Lk,...] views (fp16, last dim contiguous) -> [B,Lq,heads*64]."""
     _need_cuda(q, k, v)
@@ -234,6 +291,7 @@ def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None):
     return out
 
 
+@_timed("softmax_rows")
 def softmax_rows(s, scale, cols=None):
     """softmax(scale*s) over the last dim -> fp16, same (possibly padded) layout.  `cols` = valid
     columns when the last dim is padded (row stride = s.shape[-1])."""
@@ -249,6 +307,7 @@ def softmax_rows(s, scale, cols=None):
 
 
 # ------------------------------------------------------------------------------ elementwise
+@_timed("upsample")
 def upsample_nearest(x, out_hw):
     _need_cuda(x)
     assert x.is_contiguous()
@@ -260,6 +319,7 @@ def upsample_nearest(x, out_hw):
     return y
 
 
+@_timed("misc")
 def timestep_embedding(t, dim):
     _need_cuda(t)
     assert t.dtype == F32 and t.is_contiguous()
@@ -269,6 +329,7 @@ def timestep_embedding(t, dim):
     return out
 
 
+@_timed("misc")
 def pointwise_nchw(in1, a1, wm, bias, in2=None, a2=0.0, cin=None):
     """out[n,co] = sum_ci wm[co,ci]*(a1*in1[n,ci] + a2*in2[n,ci]) + bias[co]; fp32 NCHW, C<=8."""
     _need_cuda(in1)
@@ -282,6 +343,7 @@ def pointwise_nchw(in1, a1, wm, bias, in2=None, a2=0.0, cin=None):
     return out
 
 
+@_timed("misc")
 def decode_post(x, normals=False, sign=1.0):
     _need_cuda(x)
     assert x.dtype == F32 and x.is_contiguous() and x.shape[1] == 3
@@ -292,6 +354,7 @@ def decode_post(x, normals=False, sign=1.0):
     return out
 
 
+@_timed("cast")
 def cast_f16(x):
     _need_cuda(x)
     assert x.dtype == F32 and x.is_contiguous()
@@ -300,6 +363,7 @@ def cast_f16(x):
     return y
 
 
+@_timed("misc")
 def nhwc_to_nchw_f32(x):
     _need_cuda(x)
     assert x.is_contiguous()

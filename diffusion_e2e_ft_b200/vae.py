@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from . import ops
 from .modules import (ConfigDict, ConvInSmall, ConvOutSmall, Downsample2D, Packed, ResnetBlock2D,
-                      Upsample2D, _f16, _f32)
+                      Upsample2D, _f16, _f32, _view_cs)
 from .ops import F16, F32
 
 _DEFAULTS = dict(in_channels=3, out_channels=3, latent_channels=4,
@@ -53,8 +53,9 @@ class VAEAttention(nn.Module):
         s = ops.linear(qk[..., :C], qk[..., C:], out=s_buf[:, :, :L])                       # [B, L, L] fp32
         p_buf = ops.softmax_rows(s_buf, C ** -0.5, cols=L)
         o = ops.linear(p_buf[:, :, :L], vt)                                                 # [B, L, C]
-        out = ops.linear(o.view(B * L, C), pk["wo"], pk["bo"], residual=x.view(B * L, C), out_dtype=sdt)
-        return out.view(B, H, W, C)
+        out = ops.linear(o.view(B * L, C), pk["wo"], pk["bo"], residual=x.view(B * L, C), out_dtype=sdt,
+                         stats_rows_per_img=L)
+        return _view_cs(out, B, H, W, C)
 
 
 class _MidBlock(nn.Module):

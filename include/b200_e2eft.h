@@ -45,7 +45,10 @@ int b200_linear(const void* A, long long lda, long long a_batch_stride,
                 const float* bias, int bias_row,
                 const void* residual, long long ld_res, long long res_batch_stride,
                 void* out, long long ldo, long long out_batch_stride, int out_f32,
-                int act, float alpha, void* stream);
+                int act, float alpha,
+                float* chan_stats /* optional [M/rows_per_img][N][2]: per-channel sum / sum of squares of
+                                     the stored values, accumulated with atomics (caller zeroes) */,
+                int rows_per_img, void* stream);
 
 /* GEGLU tile width for packed width N (weights/bias rows are interleaved per tile of this width:
  * [value rows of the tile | gate rows of the tile]); 0 = not tileable. */
@@ -68,7 +71,7 @@ int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin,
                      int stride, int Ho, int Wo, int out_mul, int out_oy, int out_ox,
                      const float* bias, const float* rowvec, long long ld_rowvec,
                      const void* residual, void* out, int out_f32, int out_nchw, int act,
-                     void* stream);
+                     float* chan_stats /* optional [NB][Cout][2], see b200_linear */, void* stream);
 
 /* Patch matrix for the small-Cin input convolutions (conv_in: 8->320, 3->128, 4->512):
  * out[pixel][tap*Cin + c] fp16, row length Kpad (zero padded).  `x` is NCHW (x_f32 ? fp32 : fp16).
@@ -88,6 +91,13 @@ int b200_group_norm_stats(const void* x1, int C1, const void* x2, int C2, int in
 int b200_group_norm_apply(const void* x1, int C1, const void* x2, int C2, int in_f32, int NB, int HW,
                           int groups, const double* sums, const float* gamma, const float* beta,
                           float eps, int silu, void* y, void* raw_copy, void* stream);
+
+/* Same, but the statistics come from per-channel sums produced by the epilogue of the kernel that wrote
+ * each source (chan_stats of b200_linear / b200_conv2d_nhwc): cs1 [NB][C1][2], cs2 [NB][C2][2] (fp32). */
+int b200_group_norm_apply_cs(const void* x1, int C1, const float* cs1, const void* x2, int C2,
+                             const float* cs2, int in_f32, int NB, int HW, int groups,
+                             const float* gamma, const float* beta, float eps, int silu, void* y,
+                             void* raw_copy, void* stream);
 
 /* LayerNorm over the last dim of [rows][C] (in_f32 ? fp32 : fp16) -> fp16.
  * Replaces BasicTransformerBlock.norm1/2/3 (attention.py:205,237,264). */

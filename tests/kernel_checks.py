@@ -108,6 +108,23 @@ def check_conv(NB=2, H=24, W=24, Cin=128, Cout=192, stride=1, pad_mode="same", s
     return err, tol or (3e-5 if out_f32 else 1e-3)
 
 
+def check_upsample_conv_phases(NB=2, H=12, W=10, C=128, seed=21):
+    """Upsample2D: nearest x2 + conv3x3 computed as four 2x2 convs on the low-res input."""
+    from diffusion_e2e_ft_b200.modules import Upsample2D
+    m = Upsample2D(C).to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        m.conv.weight.copy_((torch.randn(C, C, 3, 3, generator=g) / math.sqrt(9 * C)).half().float())
+        m.conv.bias.copy_(torch.randn(C, generator=g) * 0.1)
+    x = _rand(NB, H, W, C, seed=seed + 1, dtype=torch.float32)
+    with torch.no_grad():
+        y = m.run(x, None, torch.float32)
+        torch.cuda.synchronize()
+        up = F.interpolate(x.half().float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+        ref = F.conv2d(up, m.conv.weight, m.conv.bias, padding=1).permute(0, 2, 3, 1)
+    return rel_l2(y, ref), 1e-3
+
+
 def check_conv_in(NB=2, C=8, H=20, W=24, Cout=320, seed=3):
     """small-Cin conv = im2col kernel + GEMM, NCHW fp32 input straight from the caller."""
     x = _rand(NB, C, H, W, seed=seed, dtype=torch.float32)
@@ -139,6 +156,31 @@ def check_group_norm(NB=2, H=17, W=24, C1=320, C2=0, in_f32=False, silu=True, se
     e1 = rel_l2(y, ref)
     e2 = rel_l2(raw, xc)
     return max(e1, e2), 6e-4
+
+
+def check_gn_fused_stats(swap=True, seed=31):
+    """GroupNorm whose statistics come from the producing conv / linear epilogues (no gn_stats pass),
+    on a channel concat of a conv output (fp32) and a linear output viewed NHWC."""
+    NB, H, W, Cin = 2, 16, 24, 64
+    C1, C2 = (128, 128) if swap else (192, 64)
+    x = _rand(NB, H, W, Cin, seed=seed)
+    w = _rand(C1, Cin, 3, 3, seed=seed + 1, scale=1.0 / math.sqrt(9 * Cin))
+    b = _rand(C1, seed=seed + 2, dtype=torch.float32)
+    y1 = ops.conv2d(x, ops.pack_conv(w), C1, bias=b, out_dtype=torch.float32, stats=True)
+    a = _rand(NB * H * W, 128, seed=seed + 3)
+    w2 = _rand(C2, 128, seed=seed + 4, scale=1 / math.sqrt(128))
+    y2 = ops.linear(a, w2, None, out_dtype=torch.float32, stats_rows_per_img=H * W)
+    y2v = y2.view(NB, H, W, C2)
+    y2v._cs = y2._cs
+    assert getattr(y1, "_cs", None) is not None and getattr(y2, "_cs", None) is not None
+    C = C1 + C2
+    g = _rand(C, seed=seed + 5, dtype=torch.float32) * 0.2 + 1.0
+    bt = _rand(C, seed=seed + 6, dtype=torch.float32) * 0.2
+    out = ops.group_norm(y1, g, bt, 1e-5, 32, True, x2=y2v)
+    torch.cuda.synchronize()
+    xc = torch.cat([y1, y2v], dim=-1)
+    ref = F.silu(F.group_norm(xc.float().permute(0, 3, 1, 2), 32, g, bt, 1e-5)).permute(0, 2, 3, 1)
+    return rel_l2(out, ref), 6e-4
 
 
 def check_layer_norm(rows=1000, C=640, in_f32=True, seed=0):
@@ -265,6 +307,7 @@ CHECKS = {
     "conv_out_nchw": lambda: check_conv(Cin=128, Cout=3, out_f32=True, out_nchw=True, H=40, W=56),
     "conv_out4_nchw": lambda: check_conv(Cin=64, Cout=4, out_f32=True, out_nchw=True),
     "conv_in_im2col": check_conv_in,
+    "upsample_conv_4phase": check_upsample_conv_phases,
     "conv_swap_128_res_temb_f32": lambda: check_conv(H=40, W=40, Cin=128, Cout=128, rowvec=True, residual=True, out_f32=True),
     "conv_swap_256_shortcut": lambda: check_conv(H=24, W=24, Cin=128, Cout=256, shortcut=128),
     "conv_swap_s2": lambda: check_conv(H=32, W=32, Cin=64, Cout=128, stride=2),
@@ -280,6 +323,8 @@ CHECKS = {
     "gn_f32_concat": lambda: check_group_norm(C1=1280, C2=640, in_f32=True),
     "gn_concat_f16_nosilu": lambda: check_group_norm(C1=640, C2=320, silu=False),
     "gn_128": lambda: check_group_norm(C1=128, H=64, W=64),
+    "gn_fused_stats_swap": lambda: check_gn_fused_stats(True),
+    "gn_fused_stats_normal": lambda: check_gn_fused_stats(False),
     "ln_f32": lambda: check_layer_norm(),
     "ln_f16_1280": lambda: check_layer_norm(C=1280, in_f32=False),
     "ln_320": lambda: check_layer_norm(C=320),

@@ -12,6 +12,8 @@ if len(sys.argv) > 3:
     _l.load().b200_debug_set_flags(int(sys.argv[3]))
 if len(sys.argv) > 4:
     _l.load().b200_debug_force_block_n(int(sys.argv[4]))
+if len(sys.argv) > 5:
+    _l.load().b200_debug_set_swap(int(sys.argv[5]))
 dev = "cuda"
 g = torch.Generator(device="cpu").manual_seed(0)
 r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).half().to(dev)
@@ -22,6 +24,13 @@ if what.startswith("conv"):
     NB, H, W, Cin, Cout = cfg
     x = r(NB, H, W, Cin); w = ops.pack_conv(r(Cout, Cin, 3, 3, sc=1 / math.sqrt(9 * Cin))); b = torch.zeros(Cout, device=dev)
     fn = lambda: ops.conv2d(x, w, Cout, bias=b)
+    flops = 2 * NB * H * W * Cout * 9 * Cin
+elif what.startswith("res"):          # res16 / res32: 128->128 768^2 conv with residual, fp16 / fp32 stream
+    NB, H, W, Cin, Cout = 4, 768, 768, 128, 128
+    odt = torch.float16 if what == "res16" else torch.float32
+    x = r(NB, H, W, Cin); w = ops.pack_conv(r(Cout, Cin, 3, 3, sc=1 / math.sqrt(9 * Cin))); b = torch.zeros(Cout, device=dev)
+    resid = r(NB, H, W, Cout).to(odt)
+    fn = lambda: ops.conv2d(x, w, Cout, bias=b, residual=resid, out_dtype=odt)
     flops = 2 * NB * H * W * Cout * 9 * Cin
 elif what == "attn":
     qkv = r(8, 9216, 960)
