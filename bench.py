@@ -259,7 +259,7 @@ def run_engine(args):
 
     def timed(fn, steps, time_conv=False):
         ops.STATS.reset()
-        ops.STATS.time_kind = "conv" if time_conv else None
+        ops.STATS.time_kind = ("gemm" if args.dump_shapes else "conv") if time_conv else None
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -290,6 +290,16 @@ def run_engine(args):
     conv_ms = sum(e[0].elapsed_time(e[1]) for e in stats.events)
     conv_flops = sum(e[2] for e in stats.events)
     if args.dump_shapes and rank == 0:
+        agg = {}
+        for e in stats.lin_events:
+            a = agg.setdefault(str(e[3]), [0, 0.0, 0])
+            a[0] += 1; a[1] += e[0].elapsed_time(e[1]); a[2] += e[2]
+        rows = sorted(((k, n, ms_, fl / (ms_ / 1e3) / 1e12) for k, (n, ms_, fl) in agg.items()), key=lambda r: -r[2])
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'linear_shapes.txt'), 'w') as f:
+            f.write('(B,M,N,K,act,residual,out) launches total_ms TFLOP/s\n')
+            for k, n, ms_, tf in rows:
+                f.write(f'{k:55s} {n:4d} {ms_:9.3f} {tf:8.1f}\n')
         agg = {}
         for e in stats.events:
             a = agg.setdefault(str(e[3]), [0, 0.0, 0])

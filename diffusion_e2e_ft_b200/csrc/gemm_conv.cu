@@ -81,12 +81,12 @@ int sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------
-template <int BN, typename OutT, bool SWAP>
+template <int BN, typename OutT, bool SWAP, bool GEGLU = false>
 static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
                       const GemmParams& p, cudaStream_t st) {
   using S = GemmSmem<BN>;
   static bool configured = false;
-  auto kern = gemm_conv_kernel<BN, OutT, SWAP>;
+  auto kern = gemm_conv_kernel<BN, OutT, SWAP, GEGLU>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes);
     if (e != cudaSuccess) {
@@ -111,6 +111,17 @@ static int launch_bn(int bn, bool swap, const CUtensorMap& a, const CUtensorMap&
       case 128: return launch_one<128, OutT, true>(a, a2, b, p, st);
       case 256: return launch_one<256, OutT, true>(a, a2, b, p, st);
     }
+  } else if (p.act == ACT_GEGLU) {
+    if constexpr (std::is_same<OutT, __half>::value) {
+      switch (bn) {
+        case 64: return launch_one<64, OutT, false, true>(a, a2, b, p, st);
+        case 128: return launch_one<128, OutT, false, true>(a, a2, b, p, st);
+        case 160: return launch_one<160, OutT, false, true>(a, a2, b, p, st);
+        case 256: return launch_one<256, OutT, false, true>(a, a2, b, p, st);
+      }
+    }
+    set_last_error("GEGLU epilogue needs fp16 output and a tile width in {64,128,160,256} (got %d)", bn);
+    return -1;
   } else {
     switch (bn) {
       case 32: return launch_one<32, OutT, false>(a, a2, b, p, st);
@@ -181,7 +192,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.a_batched = (a_batch_stride != 0 && batch > 1);
   p.b_batched = (w_batch_stride != 0 && batch > 1);
   // tile shape: normal (rows = 128 pixels, bn channels) vs swapped (rows = 128 channels, bn pixels)
-  const bool can_swap = g_swap_mode && N >= 128 && act != ACT_GEGLU && !bias_row && batch == 1;
+  const bool can_swap = g_swap_mode && N >= 128 && act != ACT_GEGLU && !bias_row;
   bool swap = false;
   int bn = 0;
   double best = 1e30;
@@ -201,7 +212,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
       for (int i = 0; i < 3; ++i) {
         if (g_force_bn && pc[i] != g_force_bn) continue;
         if (chan_stats && rows_per_img % pc[i] != 0) continue;
-        double c = tiles_cost((long long)((M + pc[i] - 1) / pc[i]) * ((N + 127) / 128), pc[i]) * 0.85;  // cheaper epilogue, fewer barrier round trips
+        double c = tiles_cost((long long)batch * ((M + pc[i] - 1) / pc[i]) * ((N + 127) / 128), pc[i]) * 0.85;  // cheaper epilogue, fewer barrier round trips
         if (c < best - 1e-9) { best = c; bn = pc[i]; swap = true; }
       }
     }

@@ -12,7 +12,8 @@
 //   ResnetBlock2D 1x1 `conv_shortcut` into conv2's accumulation.
 // * One elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16); accumulators are double
 //   buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
-// * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+// * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue: two warps
+//   per TMEM lane quadrant taking alternate 32-column chunks (the epilogue is latency-bound per warp).
 // * Persistent: grid = min(#tiles, #SMs), static round-robin tile schedule (n fastest).
 #pragma once
 #include <type_traits>
@@ -24,7 +25,8 @@ namespace b200 {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;       // 64 x fp16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int kEpiWarps = 8;
 constexpr int kAccStages = 2;
 constexpr int kAccStrideCols = 256;
 constexpr int kMaxTaps = 9;
@@ -69,8 +71,8 @@ struct GemmSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kStagingBytes = 4 * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose tile
-  static constexpr int kRowMetaBytes = 4 * 640;           // per-warp: out offsets, residual offsets, row bias
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose tile
+  static constexpr int kRowMetaBytes = kEpiWarps * 640;           // per-warp: out offsets, residual offsets, row bias
   static constexpr int kEpiBytes = kStagingBytes + kRowMetaBytes;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kBarrierBytes - kEpiBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
@@ -115,8 +117,19 @@ __device__ __forceinline__ void load_chunk8<__half>(const __half* src, float* v)
 }
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): 2 MUFU + ~10 FMA per element
+// instead of the ~45-instruction two-branch libdevice erff.
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = __expf(-z * z);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);          // erf(|x|/sqrt2)
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
 }
 
 // SWAP = false: accumulator rows (TMEM lanes) = 128 pixels, columns = BLOCK_N output channels.
@@ -125,7 +138,7 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 //               layer then issues 128x256 MMAs (half the operand smem traffic and half the per-k-block
 //               barrier round trips of 128x128), and since lanes = channels the NHWC stores of one
 //               accumulator column are contiguous — no smem transpose in the epilogue.
-template <int BLOCK_N, typename OutT, bool SWAP>
+template <int BLOCK_N, typename OutT, bool SWAP, bool GEGLU>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -166,7 +179,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -266,6 +279,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // residual load / output store of a row segment is one fully coalesced 128-byte (fp32) access.
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
+    const int eg = (warp - 2) >> 2;                  // epilogue group: which half of the chunks
+    const int ew = warp - 2;                         // epilogue warp index 0..7
     if constexpr (SWAP) {
       // ------------------------------------------------------------------ swapped: lane = channel
       OutT* __restrict__ out = reinterpret_cast<OutT*>(p.out);
@@ -289,7 +304,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         uint32_t* t_out = tab + acc * (2 * BLOCK_N);
         uint32_t* t_res = t_out + BLOCK_N;
-        for (int pi = et; pi < BLOCK_N; pi += 128) {
+        for (int pi = et; pi < BLOCK_N; pi += 32 * kEpiWarps) {
           bool ok;
           long long orow;
           if (p.conv) {
@@ -306,7 +321,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           t_out[pi] = ok ? (uint32_t)(orow * p.ldo) : 0xFFFFFFFFu;
           t_res[pi] = (uint32_t)(orow * p.ld_res);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");             // table visible to the 4 epilogue warps
+        asm volatile("bar.sync 1, 256;" ::: "memory");             // table visible to the 8 epilogue warps
         const int ch = n_blk * kBlockM + row_in_tile;
         const bool ch_ok = ch < p.N;
         float add = 0.f;
@@ -324,7 +339,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t t_row = tmem_base + acc * kAccStrideCols + ((uint32_t)(quad * 32) << 16);
         if (!(p.debug & 16)) {
 #pragma unroll 1
-          for (int c = 0; c < BLOCK_N; c += 32) {
+          for (int c = eg * 32; c < BLOCK_N; c += 64) {
             uint32_t roff[32];
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
@@ -384,10 +399,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     } else {
-    float (*stg)[33] = reinterpret_cast<float (*)[33]>(stage_smem + quad * (32 * 33 * 4));
+    float (*stg)[33] = reinterpret_cast<float (*)[33]>(stage_smem + ew * (32 * 33 * 4));
     // per-warp row tables (16-byte aligned): element offsets of each of the warp's 32 rows relative to the
     // batch base (0xFFFFFFFF = row outside the tensor), same for the residual, and the per-row bias
-    uint32_t* s_off_out = reinterpret_cast<uint32_t*>(rowmeta_smem + quad * 640);
+    uint32_t* s_off_out = reinterpret_cast<uint32_t*>(rowmeta_smem + ew * 640);
     uint32_t* s_off_res = s_off_out + 32;
     float* s_bias_r = reinterpret_cast<float*>(s_off_res + 32);
     int acc = 0;
@@ -438,6 +453,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       if (p.debug & 16) {
       } else if (p.out_nchw) {
+        if (eg == 0) {
         // tiny Cout (<= 8): thread = pixel, consecutive lanes = consecutive pixels -> already coalesced
         uint32_t r[16];
         tmem_ld_32x16(t_row, r);
@@ -455,8 +471,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        }
       } else {
-        const bool geglu = p.act == ACT_GEGLU;
+        constexpr bool geglu = GEGLU;                               // compile-time: keeps registers < 168
         const int width = geglu ? kOutCols / 2 : kOutCols;          // output columns this tile produces
         const int ncol0 = n_blk * width;
         const int n_out = geglu ? p.N / 2 : p.N;
@@ -474,8 +491,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           // residual rows for this chunk: 32 independent coalesced loads in flight per warp, issued
           // before the TMEM load / transpose so their latency is hidden
-          OutT rres[32];
-          if (res_b != nullptr && !geglu) {
+          OutT rres[geglu ? 1 : 32];
+          if constexpr (!geglu) if (res_b != nullptr) {
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
               const uint4 t4 = reinterpret_cast<const uint4*>(s_off_res)[q4];
@@ -490,19 +507,20 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[CW];
           if constexpr (CW == 32) tmem_ld_32x32(t_row + c, r); else tmem_ld_32x16(t_row + c, r);
           tmem_ld_wait();
-          if (geglu) {
-            // value half is in r; fetch the gate half and combine per row before the transpose
+          float gact[geglu ? 32 : 1];
+          if constexpr (geglu) {
+            // gate half first: transpose it, add its bias and apply erf-GELU with lane = column (batched,
+            // branch-free); the value half then goes through the normal transposed path below
             uint32_t g[CW];
             if constexpr (CW == 32) tmem_ld_32x32(t_row + width + c, g); else tmem_ld_32x16(t_row + width + c, g);
             tmem_ld_wait();
-            const float* __restrict__ bv = bias + n_blk * kOutCols + c;
-            const float* __restrict__ bg = bv + width;
 #pragma unroll
-            for (int e = 0; e < CW; ++e) {
-              const float v = __uint_as_float(r[e]) + bv[e];
-              const float gg = __uint_as_float(g[e]) + bg[e];
-              r[e] = __float_as_uint(v * gelu_erf_f(gg));
-            }
+            for (int e = 0; e < CW; ++e) stg[lane][e] = __uint_as_float(g[e]);
+            __syncwarp();
+            const float bg = (lane < CW) ? bias[n_blk * kOutCols + width + c + lane] : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) gact[rr] = gelu_erf_f(stg[rr][lane] + bg);
+            __syncwarp();
           }
 #pragma unroll
           for (int e = 0; e < CW; ++e) stg[lane][e] = __uint_as_float(r[e]);
@@ -511,7 +529,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float vals[32];
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) vals[rr] = stg[rr][lane];
-          if (!geglu) {
+          if constexpr (geglu) {
+            const float bv = (lane < CW) ? bias[n_blk * kOutCols + c + lane] : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) vals[rr] = (vals[rr] + bv) * gact[rr];
+          } else {
             float add = 0.f;
             if (col_ok) {
               if (bias && !p.bias_row) add += bias[col];
@@ -554,10 +576,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
         };
-        int c = 0;
 #pragma unroll 1
-        for (; c + 32 <= width; c += 32) do_chunk(c, std::integral_constant<int, 32>{});
-        if (c < width) do_chunk(c, std::integral_constant<int, 16>{});
+        for (int c = eg * 32; c < width; c += 64) {
+          if (c + 32 <= width) do_chunk(c, std::integral_constant<int, 32>{});
+          else do_chunk(c, std::integral_constant<int, 16>{});
+        }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
       tc_fence_before();

@@ -66,7 +66,17 @@ __global__ void gn_stats_kernel(const T* __restrict__ x1, int C1, const T* __res
   const T* base = second ? x2 + (long long)n * HW * C2 + (c0 - C1) : x1 + (long long)n * HW * C1 + c0;
   const int ld = second ? C2 : C1;
   if (r < rpb) {
-    for (int p = p0 + r; p < p1; p += rpb) {
+    int p = p0 + r;
+    for (; p + 3 * rpb < p1; p += 4 * rpb) {
+      float f[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(base + (long long)(p + u * rpb) * ld, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s[e] += f[u][e]; q[e] += f[u][e] * f[u][e]; }
+    }
+    for (; p < p1; p += rpb) {
       float f[8];
       load8(base + (long long)p * ld, f);
 #pragma unroll
@@ -146,13 +156,31 @@ __global__ void gn_apply_kernel(const T* __restrict__ x1, int C1, const T* __res
   const int p1 = min(HW, p0 + pix_per_cta);
   __half* yb = y + (long long)n * HW * C + c0;
   __half* rb = raw ? raw + (long long)n * HW * C + c0 : nullptr;
-  for (int p = p0 + r; p < p1; p += rpb) {
+  // 4 pixels per iteration: four independent 16-byte loads in flight per thread (latency-bound otherwise)
+  int p = p0 + r;
+  for (; p + 3 * rpb < p1; p += 4 * rpb) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(base + (long long)(p + u * rpb) * ld, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = f[u][e] * a[e] + b[e];
+        o[e] = silu ? __fdividef(t, 1.0f + __expf(-t)) : t;
+      }
+      store8h(yb + (long long)(p + u * rpb) * C, o);
+      if (rb) store8h(rb + (long long)(p + u * rpb) * C, f[u]);
+    }
+  }
+  for (; p < p1; p += rpb) {
     float f[8], o[8];
     load8(base + (long long)p * ld, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float t = f[e] * a[e] + b[e];
-      o[e] = silu ? t / (1.0f + __expf(-t)) : t;
+      o[e] = silu ? __fdividef(t, 1.0f + __expf(-t)) : t;
     }
     store8h(yb + (long long)p * C, o);
     if (rb) store8h(rb + (long long)p * C, f);

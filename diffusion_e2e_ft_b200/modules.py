@@ -320,8 +320,12 @@ class ConvOutSmall:
 
     def run(self, x):
         norm, conv = self.norm, self.conv
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        direct = cout <= 8 and cin % 64 == 0
         pk = self._pk.get([norm.weight, norm.bias, conv.weight, conv.bias],
-                          lambda: dict(g=_f32(norm.weight), b=_f32(norm.bias),
-                                       w=ops.pack_conv(conv.weight), cb=_f32(conv.bias)))
+                          lambda: dict(g=_f32(norm.weight), b=_f32(norm.bias), cb=_f32(conv.bias),
+                                       w=ops.pack_conv_small_cout(conv.weight) if direct else ops.pack_conv(conv.weight)))
         a = ops.group_norm(x, pk["g"], pk["b"], norm.eps, norm.num_groups, True)
-        return ops.conv2d(a, pk["w"], conv.weight.shape[0], bias=pk["cb"], out_dtype=F32, out_nchw=True)
+        if direct:
+            return ops.conv3x3_small_cout(a, pk["w"], pk["cb"], cout)      # input read once (halo tile in smem)
+        return ops.conv2d(a, pk["w"], cout, bias=pk["cb"], out_dtype=F32, out_nchw=True)

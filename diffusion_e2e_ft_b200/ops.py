@@ -30,6 +30,7 @@ class Stats:
         self.flops = {"conv": 0, "linear": 0, "attn": 0}
         self.count = {"conv": 0, "linear": 0, "attn": 0}
         self.events = []               # (start, end, flops)
+        self.lin_events = []
 
     def add(self, kind=None, flops=0):
         self.launches += 1
@@ -38,7 +39,7 @@ class Stats:
             self.count[kind] += 1
 
     def timed(self, kind):
-        return self.time_kind == kind
+        return self.time_kind == kind or self.time_kind == "gemm"
 
 
 STATS = Stats()
@@ -153,6 +154,10 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
     if (FUSE_GN_STATS and stats_rows_per_img and not batched and stats_rows_per_img % 64 == 0
             and M % stats_rows_per_img == 0 and (N >= 128 or stats_rows_per_img % 128 == 0)):
         cs = _new_stats(M // stats_rows_per_img, n_out, a.device)
+    ev = None
+    if STATS.timed("linear"):
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     rc = _lib.load().b200_linear(
         _p(a), a.stride(-2), a.stride(0) if a.dim() == 3 else 0,
         _p(w), w.stride(-2), (w.stride(0) if w.dim() == 3 else 0),
@@ -163,6 +168,10 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
         act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _stream())
     _lib.check(rc, "b200_linear")
     STATS.add("linear", 2 * B * M * N * K)
+    if ev is not None:
+        ev[1].record()
+        STATS.lin_events.append((ev[0], ev[1], 2 * B * M * N * K,
+                                 (B, M, N, K, act, residual is not None, str(out.dtype)[6:])))
     if cs is not None:
         out._cs = cs
     return out
@@ -214,6 +223,30 @@ def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, r
     STATS.add("conv", fl)
     if cs is not None:
         out._cs = cs
+    return out
+
+
+def pack_conv_small_cout(w):
+    """[Cout<=8, C, 3, 3] -> fp16 [C/64][9][4][8][16]: per 64-channel chunk, tap, 16-channel k-step the B
+    fragment rows (n = output channel, zero padded to 8) of mma.m16n8k16."""
+    cout, c = w.shape[0], w.shape[1]
+    assert cout <= 8 and c % 64 == 0
+    wp = torch.zeros(8, c, 3, 3, dtype=F32, device=w.device)
+    wp[:cout] = w.detach().float()
+    wp = wp.permute(2, 3, 0, 1).reshape(9, 8, c // 64, 4, 16)        # [tap][n][chunk][ks][k]
+    return wp.permute(2, 0, 3, 1, 4).contiguous().to(F16)             # [chunk][tap][ks][n][k]
+
+
+@_timed("conv_small")
+def conv3x3_small_cout(x, wq, bias, cout):
+    """x NHWC fp16 -> NCHW fp32 [NB, cout, H, W]."""
+    _need_cuda(x, wq)
+    assert x.dtype == F16 and x.is_contiguous() and wq.dtype == F16 and wq.is_contiguous()
+    NB, H, W, C = x.shape
+    out = torch.empty((NB, cout, H, W), dtype=F32, device=x.device)
+    _ck(_lib.load().b200_conv3x3_small_cout(_p(x), NB, H, W, C, _p(wq), _p(bias), cout, _p(out), _stream()),
+        "b200_conv3x3_small_cout")
+    STATS.flops["conv"] += 2 * NB * H * W * cout * 9 * C
     return out
 
 

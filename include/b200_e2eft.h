@@ -73,6 +73,12 @@ int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin,
                      const void* residual, void* out, int out_f32, int out_nchw, int act,
                      float* chan_stats /* optional [NB][Cout][2], see b200_linear */, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution with Cout <= 8 (the `conv_out` layers: unet_2d_condition.py:617-619
+ * and the VAE encoder/decoder conv_out): NHWC fp16 in (C % 64 == 0), NCHW fp32 out, input read once.
+ * wq: fp16 [C/64][9 taps][4 k-steps][8 n][16 k] (zero padded to 8 output channels). */
+int b200_conv3x3_small_cout(const void* x, int NB, int H, int W, int C, const void* wq,
+                            const float* bias, int Cout, float* out, void* stream);
+
 /* Patch matrix for the small-Cin input convolutions (conv_in: 8->320, 3->128, 4->512):
  * out[pixel][tap*Cin + c] fp16, row length Kpad (zero padded).  `x` is NCHW (x_f32 ? fp32 : fp16).
  * Serves unet_2d_condition.py:294-296,1084 and the VAE conv_in. */

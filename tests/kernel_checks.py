@@ -125,6 +125,16 @@ def check_upsample_conv_phases(NB=2, H=12, W=10, C=128, seed=21):
     return rel_l2(y, ref), 1e-3
 
 
+def check_conv_small_cout(NB=2, H=37, W=50, C=128, Cout=3, seed=41):
+    x = _rand(NB, H, W, C, seed=seed)
+    w = _rand(Cout, C, 3, 3, seed=seed + 1, scale=1.0 / math.sqrt(9 * C))
+    b = _rand(Cout, seed=seed + 2, dtype=torch.float32)
+    out = ops.conv3x3_small_cout(x, ops.pack_conv_small_cout(w), b, Cout)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)
+    return rel_l2(out, ref), 3e-5
+
+
 def check_conv_in(NB=2, C=8, H=20, W=24, Cout=320, seed=3):
     """small-Cin conv = im2col kernel + GEMM, NCHW fp32 input straight from the caller."""
     x = _rand(NB, C, H, W, seed=seed, dtype=torch.float32)
@@ -307,6 +317,9 @@ CHECKS = {
     "conv_out_nchw": lambda: check_conv(Cin=128, Cout=3, out_f32=True, out_nchw=True, H=40, W=56),
     "conv_out4_nchw": lambda: check_conv(Cin=64, Cout=4, out_f32=True, out_nchw=True),
     "conv_in_im2col": check_conv_in,
+    "conv_small_cout_3": check_conv_small_cout,
+    "conv_small_cout_4_320": lambda: check_conv_small_cout(NB=1, H=96, W=96, C=320, Cout=4),
+    "conv_small_cout_8_512": lambda: check_conv_small_cout(NB=2, H=12, W=20, C=512, Cout=8),
     "upsample_conv_4phase": check_upsample_conv_phases,
     "conv_swap_128_res_temb_f32": lambda: check_conv(H=40, W=40, Cin=128, Cout=128, rowvec=True, residual=True, out_f32=True),
     "conv_swap_256_shortcut": lambda: check_conv(H=24, W=24, Cin=128, Cout=256, shortcut=128),

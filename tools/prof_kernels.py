@@ -40,9 +40,16 @@ elif what == "gn":
     x = r(4, 768, 768, 128); gm = torch.ones(128, device=dev); bt = torch.zeros(128, device=dev)
     fn = lambda: ops.group_norm(x, gm, bt, 1e-6)
     flops = 0
+elif what == "geglu":
+    pass
 elif what == "linear":
     a = r(73728, 320); w = r(2560, 320, sc=0.05); b = torch.zeros(2560, device=dev)
     fn = lambda: ops.linear(a, w, b)
+    flops = 2 * 73728 * 320 * 2560
+if what == "geglu":
+    a = r(73728, 320); w0 = r(2560, 320, sc=0.05); b0 = torch.zeros(2560, device=dev)
+    wg, bg = ops.pack_geglu(w0, b0)
+    fn = lambda: ops.linear(a, wg, bg, act=ops.ACT_GEGLU)
     flops = 2 * 73728 * 320 * 2560
 for _ in range(2):
     fn()
