@@ -62,10 +62,11 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = k_full + kKvStages;
   uint64_t* kv_empty = v_full + kKvStages;
-  uint64_t* s_full = kv_empty + kKvStages;              // [kWG]
-  uint64_t* p_full = s_full + kWG;
-  uint64_t* o_full = p_full + kWG;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + kWG);
+  uint64_t* s_full = kv_empty + kKvStages;              // [kWG][2]  S buffer filled by QK^T
+  uint64_t* o_full = s_full + 2 * kWG;                  // [kWG][2]  T = P V landed (aliases S buffer cols 0..63)
+  uint64_t* p_full = o_full + 2 * kWG;                  // [kWG]     P written, S buffer fully read
+  uint64_t* t_empty = p_full + kWG;                     // [kWG]     T folded into O -> its S buffer is reusable
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + kWG);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,9 +88,12 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&kv_empty[i], 1);
     }
     for (int i = 0; i < kWG; ++i) {
-      mbar_init(&s_full[i], 1);
+      mbar_init(&s_full[2 * i], 1);
+      mbar_init(&s_full[2 * i + 1], 1);
+      mbar_init(&o_full[2 * i], 1);
+      mbar_init(&o_full[2 * i + 1], 1);
       mbar_init(&p_full[i], kBq);
-      mbar_init(&o_full[i], 1);
+      mbar_init(&t_empty[i], kBq);
     }
     fence_barrier_init();
   }
@@ -98,8 +102,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tS = tmem_base;            // S[w]: columns [128w, 128w+128)
-  const uint32_t tO = tmem_base + 256;      // T[w]: columns [256+64w, 256+64w+64)
+  // TMEM: S[w][buf] at columns 256w + 128buf (+128); T_j = P_j V_j is written over columns 0..63 of the
+  // S buffer it was computed from (dead once P_j is in smem), so S can be double buffered within 512 columns
+  const uint32_t tS = tmem_base;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -126,15 +131,15 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     constexpr uint32_t idesc_qk = make_idesc_f16(kBq, kBk, 0, 0);
     constexpr uint32_t idesc_pv = make_idesc_f16(kBq, kD, 0, 1);   // B (=V) is MN-major
     mbar_wait(q_full, 0);
-    auto issue_qk = [&](int j, int w) {            // S[w] = Q[w] K_j^T
+    auto issue_qk = [&](int j, int w) {            // S[w][j&1] = Q[w] K_j^T
       if (lane == 0) {
         const int st = j % kKvStages;
         const uint64_t qdesc = make_desc_sw128(smem_u32(sQ + w * kTileBytes), 16, 1024);
         const uint64_t kdesc = make_desc_sw128(smem_u32(sK + st * kTileBytes), 16, 1024);
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k)
-          umma_f16(tS + w * kBk, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[w]);
+          umma_f16(tS + w * 256 + (j & 1) * kBk, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[2 * w + (j & 1)]);
       }
       __syncwarp();
     };
@@ -144,8 +149,17 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     issue_qk(0, 1);
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j % kKvStages;
+      // next S tiles first: they only need the buffer that held T_{j-1} to be drained
+      if (j + 1 < n_tiles) {
+        mbar_wait(&k_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
+        for (int w = 0; w < kWG; ++w) {
+          if (j >= 1) mbar_wait(&t_empty[w], (j - 1) & 1);
+          tc_fence_after();
+          issue_qk(j + 1, w);
+        }
+      }
       for (int w = 0; w < kWG; ++w) {
-        mbar_wait(&p_full[w], j & 1);               // P[w](j) in smem, S[w] and T[w] drained by WG w
+        mbar_wait(&p_full[w], j & 1);               // P[w](j) in smem, S[w][j&1] fully read by WG w
         if (w == 0) mbar_wait(&v_full[st], (j / kKvStages) & 1);
         tc_fence_after();
         if (lane == 0) {
@@ -157,18 +171,11 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint64_t pdesc = make_desc_sw128(pbase + (k >> 2) * (kBq * 128) + (k & 3) * 32, 16, 1024);
             // B = V[16k..16k+16, :]: MN-major, 16 key rows = 2 groups of 8 rows (SBO = 1024 B)
             const uint64_t vdesc = make_desc_sw128(vbase + k * 2048, 16, 1024);
-            umma_f16(tO + w * kD, pdesc, vdesc, idesc_pv, k != 0);
+            umma_f16(tS + w * 256 + (j & 1) * kBk, pdesc, vdesc, idesc_pv, k != 0);
           }
-          umma_commit(&o_full[w]);
+          umma_commit(&o_full[2 * w + (j & 1)]);
         }
         __syncwarp();
-        if (j + 1 < n_tiles) {
-          if (w == 0) {
-            mbar_wait(&k_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
-            tc_fence_after();
-          }
-          issue_qk(j + 1, w);
-        }
       }
       if (lane == 0) umma_commit(&kv_empty[st]);     // K_j / V_j slot reusable once everything above retires
       __syncwarp();
@@ -179,8 +186,7 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int quad = warp & 3;                       // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const uint32_t ts = tS + w * kBk + lane_off;
-    const uint32_t to = tO + w * kD + lane_off;
+    const uint32_t ts_base = tS + w * 256 + lane_off;
     float o[kD];
 #pragma unroll
     for (int i = 0; i < kD; ++i) o[i] = 0.f;
@@ -192,8 +198,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int j = 0; j < n_tiles; ++j) {
       const int jj = j % tiles_per_seg;
       const int valid = min(kBk, p.Lk - jj * kBk);
-      mbar_wait(&s_full[w], j & 1);
+      mbar_wait(&s_full[2 * w + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
+      const uint32_t ts = ts_base + (j & 1) * kBk;
       // ---- pass 1: row max
       float mx0 = -INFINITY, mx1 = -INFINITY;
       if (valid == kBk) {
@@ -224,8 +231,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float mc = m_new * c;
       // ---- fold the previous tile's P V product into O (T[w] must be drained before PV(j) is issued)
       if (j > 0) {
-        mbar_wait(&o_full[w], (j - 1) & 1);
+        mbar_wait(&o_full[2 * w + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
         tc_fence_after();
+        const uint32_t to = ts_base + ((j - 1) & 1) * kBk;
 #pragma unroll
         for (int cc = 0; cc < kD; cc += 32) {
           uint32_t r[32];
@@ -234,6 +242,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int e = 0; e < 32; ++e) o[cc + e] = fmaf(o[cc + e], alpha_prev, __uint_as_float(r[e]));
         }
+        tc_fence_before();
+        mbar_arrive(&t_empty[w]);        // the buffer that held S_{j-1} / T_{j-1} may take S_{j+1}
       }
       // ---- pass 2: P = exp2(S*c - m*c) -> fp16 smem (SWIZZLE_128B K-major A operand), row sum
       float rs0 = 0.f, rs1 = 0.f;
@@ -280,14 +290,15 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       l = fmaf(l, alpha, rs0 + rs1);
       m = m_new;
       alpha_prev = alpha;
-      tc_fence_before();          // our TMEM reads (S[w], T[w]) are done before the MMA warp overwrites them
+      tc_fence_before();          // our TMEM reads of S[w][j&1] are done before P V overwrites its first 64 columns
       fence_proxy_async_smem();   // P visible to the tensor-core (async) proxy
       mbar_arrive(&p_full[w]);
     }
     {
       const int j = n_tiles - 1;
-      mbar_wait(&o_full[w], j & 1);
+      mbar_wait(&o_full[2 * w + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
+      const uint32_t to = ts_base + (j & 1) * kBk;
 #pragma unroll
       for (int cc = 0; cc < kD; cc += 32) {
         uint32_t r[32];

@@ -116,3 +116,38 @@ def run_unet_fullwidth(device="cuda:0", latent=24, batch=1, stream_dtype=torch.f
     y16 = ref16(x.half().to(device), 999, ctx.half().to(device)).sample
     out["torch_fp16_rel_l2"] = rel_l2(y16, want)
     return out
+
+
+@torch.no_grad()
+def run_full_size(device="cuda:0", res=768, batch=1, stream_dtype=torch.float32):
+    """BASELINE.json full size: 768x768, SD-2 widths.  The oracle itself is run in fp32 on the GPU with plain
+    torch ops (test infrastructure) so the comparison finishes in seconds; also checks size-independent
+    properties (range of depth, unit normals, batch consistency)."""
+    from oracle.unet import UNet2DConditionRef, UNetConfig, seeded_init
+    from oracle.vae import AutoencoderKLRef, VAEConfig
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    uref = seeded_init(UNet2DConditionRef(UNetConfig()), seed=4321).eval()
+    vref = seeded_init(AutoencoderKLRef(VAEConfig()), seed=99).eval()
+    unet, vae = engine_from_oracle(uref, vref, device, stream_dtype)
+    uref, vref = uref.to(device), vref.to(device)
+    g = torch.Generator().manual_seed(7)
+    rgb = (torch.rand(batch, 3, res, res, generator=g) * 2 - 1).to(device)
+    ete = (torch.randn(1, 2, 1024, generator=g) * 0.5).to(device)
+    want, lat = OP.marigold_single_infer(uref, vref, OP.DDIMOneStep(), rgb, ete, return_latents=True)
+    pipe = MarigoldPipeline(unet, vae, DDIMScheduler(), empty_text_embed=ete)
+    got = pipe.single_infer(rgb, 1, False, noise="zeros")
+    out = dict(depth_rel_l2=rel_l2(got, want))
+    out["rgb_latent_rel_l2"] = rel_l2(pipe.encode_rgb(rgb), lat["rgb_latent"])
+    x = torch.cat([lat["rgb_latent"], torch.zeros_like(lat["rgb_latent"])], 1)
+    out["unet_rel_l2"] = rel_l2(unet(x, 999, ete.repeat(batch, 1, 1)).sample, lat["unet_out"])
+    out["decode_rel_l2"] = rel_l2(vae.decode_from_prediction(lat["unet_out"], -float((1 - OP.DDIMOneStep().alphas_cumprod[999]).sqrt())),
+                                  lat["decoded"])
+    out.update(absrel_protocol(got, want))
+    out["depth_min"], out["depth_max"] = got.min().item(), got.max().item()
+    nrm = pipe.single_infer(rgb, 1, False, noise="zeros", normals=True)
+    out["normals_norm_err"] = (nrm.float().norm(dim=1) - 1).abs().max().item()
+    # batch consistency: the same image twice in one batch gives the same answer as alone
+    two = pipe.single_infer(torch.cat([rgb[:1], rgb[:1]]), 1, False, noise="zeros")
+    out["batch_consistency"] = max(rel_l2(two[0:1], got[0:1]), rel_l2(two[1:2], got[0:1]))
+    return out

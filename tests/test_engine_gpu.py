@@ -58,3 +58,17 @@ def test_ensemble_normals_index_bit_exact_on_gpu():
     got, _ = ensemble_normals(preds.cuda())
     nrm = preds / (torch.norm(preds, p=2, dim=1).unsqueeze(1) + 1e-5)
     assert torch.equal(got.cpu(), nrm[idx]) or torch.allclose(got.cpu(), nrm[idx], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_full_size_768_against_fp32_oracle_on_gpu():
+    """BASELINE.json configs[0]/[1] size (3x768x768, SD-2 widths): engine vs the fp32 oracle (run with torch ops
+    on the same GPU), plus size-independent properties."""
+    r = EC.run_full_size(res=768, batch=1)
+    print(r)
+    for k in ("rgb_latent_rel_l2", "unet_rel_l2", "decode_rel_l2", "depth_rel_l2"):
+        assert r[k] <= 3e-3, (k, r)
+    assert r["absrel_delta"] <= 1e-3, r
+    assert 0.0 <= r["depth_min"] and r["depth_max"] <= 1.0, r
+    assert r["normals_norm_err"] <= 2e-3, r
+    assert r["batch_consistency"] <= 1e-3, r
