@@ -167,7 +167,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
                            const float* bias, int bias_row, const void* residual, long long ld_res,
                            long long res_batch_stride, void* out, long long ldo,
                            long long out_batch_stride, int out_f32, int act, float alpha,
-                           float* chan_stats, int rows_per_img, void* stream) {
+                           float* chan_stats, int rows_per_img, void* out2_f16, void* stream) {
   B200_CHECK_ARG(A && W && out, "b200_linear: null pointer");
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "b200_linear: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
   B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "b200_linear: lda/ldw must be multiples of 8 elements (16 B)");
@@ -228,7 +228,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.bias = bias; p.bias_row = bias_row;
   p.residual = residual; p.ld_res = ld_res; p.res_batch_stride = res_batch_stride;
   p.act = act; p.alpha = alpha; p.debug = g_debug;
-  p.chan_stats = chan_stats; p.rows_per_img = rows_per_img;
+  p.chan_stats = chan_stats; p.rows_per_img = rows_per_img; p.out2 = (__half*)out2_f16;
   p.out_mul = 1;
   p.vec_ok = 0;
 
@@ -277,7 +277,7 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
                                 const int* tap_dx, int stride, int Ho, int Wo, int out_mul, int out_oy,
                                 int out_ox, const float* bias, const float* rowvec,
                                 long long ld_rowvec, const void* residual, void* out, int out_f32,
-                                int out_nchw, int act, float* chan_stats, void* stream) {
+                                int out_nchw, int act, float* chan_stats, void* out2_f16, void* stream) {
   B200_CHECK_ARG(X && Wp && out, "b200_conv2d_nhwc: null pointer");
   B200_CHECK_ARG(Cin % 64 == 0, "b200_conv2d_nhwc: Cin=%d must be a multiple of 64 (use im2col path)", Cin);
   B200_CHECK_ARG(C2 % 64 == 0, "b200_conv2d_nhwc: C2=%d must be a multiple of 64", C2);
@@ -350,6 +350,7 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   p.residual = residual; p.ld_res = Cout;
   p.act = act; p.alpha = 1.0f; p.debug = g_debug;
   p.chan_stats = out_nchw ? nullptr : chan_stats;
+  p.out2 = out_nchw ? nullptr : (__half*)out2_f16;
   p.vec_ok = (Cout % 8 == 0) && (!residual || ((uintptr_t)residual & 15) == 0);
 
   CUtensorMap ta, ta2, tb;

@@ -60,6 +60,7 @@ struct GemmParams {
   long long ld_res, res_batch_stride;
   int act;
   float alpha;                 // scale applied to the accumulator before bias
+  __half* out2;                // optional second output: fp16 copy of `out` (same layout) for a following GEMM/conv operand
   float* chan_stats;           // optional [img][N][2] per-channel (sum, sum of squares) of the stored values
   int rows_per_img;            // LINEAR + chan_stats: img = row / rows_per_img (tiles never straddle images)
   int debug;                   // perf experiments: 1 = no epilogue stores, 2 = no A loads, 4 = no B loads, 8 = no MMAs, 16 = empty epilogue
@@ -331,6 +332,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         OutT* __restrict__ out_b = out + (long long)b * p.out_batch_stride + ch;
         const OutT* __restrict__ res_b = res ? res + (long long)b * p.res_batch_stride + ch : nullptr;
+        __half* __restrict__ out2_b = p.out2 ? p.out2 + (long long)b * p.out_batch_stride + ch : nullptr;
         if (!p.conv && p.chan_stats) img = (int)(((long long)m_blk * BLOCK_N) / p.rows_per_img);
         float st1 = 0.f, st2 = 0.f;
 
@@ -377,6 +379,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (ch_ok && roff[j] != 0xFFFFFFFFu) out_b[(size_t)roff[j]] = (OutT)vals[j];
+              if (out2_b != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (ch_ok && roff[j] != 0xFFFFFFFFu) out2_b[(size_t)roff[j]] = __float2half_rn(vals[j]);
+              }
             }
             if (p.chan_stats) {
 #pragma unroll
@@ -446,6 +453,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       OutT* __restrict__ out_b = out + (long long)b * p.out_batch_stride;
       const OutT* __restrict__ res_b = res ? res + (long long)b * p.res_batch_stride : nullptr;
+      __half* __restrict__ out2_b = p.out2 ? p.out2 + (long long)b * p.out_batch_stride : nullptr;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -559,6 +567,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr)
               if (col_ok && roff[rr] != 0xFFFFFFFFu) out_b[(size_t)roff[rr] + col] = (OutT)vals[rr];
+            if (out2_b != nullptr) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr)
+                if (col_ok && roff[rr] != 0xFFFFFFFFu) out2_b[(size_t)roff[rr] + col] = __float2half_rn(vals[rr]);
+            }
           }
           if (p.chan_stats) {
             float st1 = 0.f, st2 = 0.f;

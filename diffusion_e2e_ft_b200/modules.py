@@ -51,11 +51,15 @@ class Packed:
 
 
 def _view_cs(t, *shape):
-    """view() that keeps the fused GroupNorm channel sums (`._cs`) attached by the producing kernel."""
+    """view() that keeps the producer-attached extras: fused GroupNorm channel sums (`._cs`) and the fp16
+    twin (`._h16`)."""
     v = t.view(*shape)
     cs = getattr(t, "_cs", None)
     if cs is not None:
         v._cs = cs
+    h = getattr(t, "_h16", None)
+    if h is not None:
+        v._h16 = h.view(*shape)
     return v
 
 
@@ -100,8 +104,9 @@ class ResnetBlock2D(nn.Module):
             return d
         return self._pk.get(ps, build)
 
-    def run(self, x, temb=None, skip=None, sdt=F32):
-        """x (and optional skip, channel-concatenated after x): stream NHWC; temb: fp32 [B,cout] view."""
+    def run(self, x, temb=None, skip=None, sdt=F32, f16_copy=False):
+        """x (and optional skip, channel-concatenated after x): stream NHWC; temb: fp32 [B,cout] view.
+        `f16_copy`: the output also gets an fp16 twin (the next op is a stride-2 / upsample conv)."""
         pk = self._packed()
         if self.conv_shortcut is not None and (skip is not None or x.dtype != F16):
             # the 1x1 shortcut needs the (concatenated) input as an fp16 operand: emitted by the GN pass
@@ -113,8 +118,10 @@ class ResnetBlock2D(nn.Module):
         h = ops.conv2d(a1, pk["w1"], self.cout, bias=pk["c1b"], rowvec=temb, stats=True)
         a2 = ops.group_norm(h, pk["g2"], pk["b2"], self.eps, self.groups, True)
         if raw is not None:
-            return ops.conv2d(a2, pk["w2"], self.cout, bias=pk["c2b"], x2=raw, out_dtype=sdt, stats=True)
-        return ops.conv2d(a2, pk["w2"], self.cout, bias=pk["c2b"], residual=x, out_dtype=sdt, stats=True)
+            return ops.conv2d(a2, pk["w2"], self.cout, bias=pk["c2b"], x2=raw, out_dtype=sdt, stats=True,
+                              f16_copy=f16_copy)
+        return ops.conv2d(a2, pk["w2"], self.cout, bias=pk["c2b"], residual=x, out_dtype=sdt, stats=True,
+                          f16_copy=f16_copy)
 
 
 class Downsample2D(nn.Module):
@@ -259,7 +266,7 @@ class BasicTransformerBlock(nn.Module):
         h = ops.linear(o2.view(B * L, C), pk["wo2"], pk["bo2"], residual=h, out_dtype=sdt)
         n3 = ops.layer_norm(h, *pk["ln"][2])
         g = ops.linear(n3, pk["wg"], pk["bg"], act=ops.ACT_GEGLU)
-        return ops.linear(g, pk["wf"], pk["bf"], residual=h, out_dtype=sdt)
+        return ops.linear(g, pk["wf"], pk["bf"], residual=h, out_dtype=sdt, f16_copy=True)   # proj_out operand
 
 
 class Transformer2DModel(nn.Module):
@@ -275,7 +282,7 @@ class Transformer2DModel(nn.Module):
         self.proj_out = nn.Linear(dim, dim)
         self._pk = Packed()
 
-    def run(self, x, ctx16, sdt=F32):
+    def run(self, x, ctx16, sdt=F32, f16_copy=False):
         own = [self.norm.weight, self.norm.bias, self.proj_in.weight, self.proj_in.bias,
                self.proj_out.weight, self.proj_out.bias]
         pk = self._pk.get(own, lambda: dict(g=_f32(self.norm.weight), b=_f32(self.norm.bias),
@@ -288,7 +295,8 @@ class Transformer2DModel(nn.Module):
         for blk in self.transformer_blocks:
             h = blk.run(h, B, L, ctx16, sdt)
         h16 = h if h.dtype == F16 else ops.cast_f16(h)
-        out = ops.linear(h16, pk["wo"], pk["bo"], residual=x.view(B * L, C), out_dtype=sdt, stats_rows_per_img=L)
+        out = ops.linear(h16, pk["wo"], pk["bo"], residual=x.view(B * L, C), out_dtype=sdt, stats_rows_per_img=L,
+                         f16_copy=f16_copy)
         return _view_cs(out, B, H, W, C)
 
 

@@ -133,9 +133,10 @@ def _new_stats(nb, c, device):
 
 @_timed("gemm_linear")
 def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE, alpha=1.0,
-           bias_row=False, stats_rows_per_img=0):
+           bias_row=False, stats_rows_per_img=0, f16_copy=False):
     """`stats_rows_per_img` > 0: also accumulate per-(image, channel) sum / sum-of-squares of the output
-    (attached to the result as `._cs`) for a following GroupNorm."""
+    (attached to the result as `._cs`) for a following GroupNorm.  `f16_copy`: an fp32 output also gets an
+    fp16 twin (`._h16`) written by the same epilogue, so a following GEMM needs no cast pass."""
     """a: [M,K] or [B,M,K] fp16 (last dim contiguous); w: [N,K] or [B,N,K] fp16."""
     _need_cuda(a, w)
     assert a.dtype == F16 and w.dtype == F16 and a.stride(-1) == 1 and w.stride(-1) == 1
@@ -154,6 +155,7 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
     if (FUSE_GN_STATS and stats_rows_per_img and not batched and stats_rows_per_img % 64 == 0
             and M % stats_rows_per_img == 0 and (N >= 128 or stats_rows_per_img % 128 == 0)):
         cs = _new_stats(M // stats_rows_per_img, n_out, a.device)
+    h16 = torch.empty(out.shape, dtype=F16, device=out.device) if (f16_copy and out.dtype == F32 and out.is_contiguous()) else None
     ev = None
     if STATS.timed("linear"):
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -165,7 +167,7 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
         _p(residual), residual.stride(-2) if residual is not None else 0,
         (residual.stride(0) if (residual is not None and batched) else 0),
         _p(out), out.stride(-2), out.stride(0) if batched else 0, int(out.dtype == F32),
-        act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _stream())
+        act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _p(h16), _stream())
     _lib.check(rc, "b200_linear")
     STATS.add("linear", 2 * B * M * N * K)
     if ev is not None:
@@ -174,6 +176,8 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
                                  (B, M, N, K, act, residual is not None, str(out.dtype)[6:])))
     if cs is not None:
         out._cs = cs
+    if h16 is not None:
+        out._h16 = h16
     return out
 
 
@@ -181,7 +185,7 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
 @_timed("gemm_conv")
 def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, rowvec=None,
            residual=None, out=None, out_dtype=F16, out_nchw=False, act=ACT_NONE,
-           out_mul=1, out_off=(0, 0), stats=None):
+           out_mul=1, out_off=(0, 0), stats=None, f16_copy=False):
     """`stats`: True -> allocate, or an existing [NB,Cout,2] fp32 tensor to accumulate into; the per-channel
     sums of the output are attached to the result as `._cs` for a following GroupNorm."""
     """x: NHWC fp16 [NB,H,W,Cin]; wp: packed fp16 [Cout, len(taps)*Cin (+C2)]."""
@@ -204,6 +208,7 @@ def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, r
     cs = None
     if stats is not None and stats is not False and FUSE_GN_STATS and not out_nchw:
         cs = _new_stats(NB, cout, x.device) if stats is True else stats
+    h16 = torch.empty(out.shape, dtype=F16, device=out.device) if (f16_copy and out.dtype == F32 and not out_nchw) else None
     dy = (c_int * len(taps))(*[t[0] for t in taps])
     dx = (c_int * len(taps))(*[t[1] for t in taps])
     fl = 2 * NB * Ho * Wo * cout * (len(taps) * Cin + C2)
@@ -215,7 +220,7 @@ def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, r
         _p(x), NB, H, W, Cin, _p(x2), C2, _p(wp), cout, len(taps), dy, dx, stride, Ho, Wo,
         out_mul, out_off[0], out_off[1], _p(bias), _p(rowvec),
         rowvec.stride(0) if rowvec is not None else 0, _p(residual), _p(out),
-        int(out.dtype == F32), int(out_nchw), act, _p(cs), _stream())
+        int(out.dtype == F32), int(out_nchw), act, _p(cs), _p(h16), _stream())
     _lib.check(rc, "b200_conv2d_nhwc")
     if ev is not None:
         ev[1].record()
@@ -223,6 +228,8 @@ def conv2d(x, wp, cout, bias=None, taps=TAPS3, stride=1, out_hw=None, x2=None, r
     STATS.add("conv", fl)
     if cs is not None:
         out._cs = cs
+    if h16 is not None:
+        out._h16 = h16
     return out
 
 
@@ -389,6 +396,9 @@ def decode_post(x, normals=False, sign=1.0):
 
 @_timed("cast")
 def cast_f16(x):
+    h = getattr(x, "_h16", None)
+    if h is not None:                      # the producing epilogue already wrote the fp16 twin
+        return h
     _need_cuda(x)
     assert x.dtype == F32 and x.is_contiguous()
     y = torch.empty(x.shape, dtype=F16, device=x.device)

@@ -219,9 +219,10 @@ class B200UNet2DConditionModel(nn.Module):
         skips = [x]
         for blk in self.down_blocks:
             for i, r in enumerate(blk.resnets):
-                x = r.run(x, temb_of[id(r)], None, sdt)
+                last = (i == len(blk.resnets) - 1) and blk.downsamplers is not None    # feeds the stride-2 conv
+                x = r.run(x, temb_of[id(r)], None, sdt, f16_copy=last and blk.attentions is None)
                 if blk.attentions is not None:
-                    x = blk.attentions[i].run(x, ctx16, sdt)
+                    x = blk.attentions[i].run(x, ctx16, sdt, f16_copy=last)
                 skips.append(x)
             if blk.downsamplers is not None:
                 x = blk.downsamplers[0].run(x, sdt)
@@ -235,9 +236,10 @@ class B200UNet2DConditionModel(nn.Module):
         for bi, blk in enumerate(self.up_blocks):
             for i, r in enumerate(blk.resnets):
                 skip = skips.pop()
-                x = r.run(x, temb_of[id(r)], skip, sdt)
+                last = (i == len(blk.resnets) - 1) and blk.upsamplers is not None and not forward_size
+                x = r.run(x, temb_of[id(r)], skip, sdt, f16_copy=last and blk.attentions is None)
                 if blk.attentions is not None:
-                    x = blk.attentions[i].run(x, ctx16, sdt)
+                    x = blk.attentions[i].run(x, ctx16, sdt, f16_copy=last)
             if blk.upsamplers is not None:
                 size = tuple(skips[-1].shape[1:3]) if forward_size else None
                 x = blk.upsamplers[0].run(x, size, sdt)

@@ -117,8 +117,8 @@ class Encoder(nn.Module):
         sdt = self.stream_dtype
         h = self._in.run(x if x.dtype in (F16, F32) else x.float(), sdt)
         for blk in self.down_blocks:
-            for r in blk.resnets:
-                h = r.run(h, None, None, sdt)
+            for i, r in enumerate(blk.resnets):
+                h = r.run(h, None, None, sdt, f16_copy=(i == len(blk.resnets) - 1 and blk.downsamplers is not None))
             if blk.downsamplers is not None:
                 h = blk.downsamplers[0].run(h, sdt)
         h = self.mid_block.run(h, sdt)
@@ -152,8 +152,8 @@ class Decoder(nn.Module):
         h = self._in.run(z if z.dtype in (F16, F32) else z.float(), sdt)
         h = self.mid_block.run(h, sdt)
         for blk in self.up_blocks:
-            for r in blk.resnets:
-                h = r.run(h, None, None, sdt)
+            for i, r in enumerate(blk.resnets):
+                h = r.run(h, None, None, sdt, f16_copy=(i == len(blk.resnets) - 1 and blk.upsamplers is not None))
             if blk.upsamplers is not None:
                 h = blk.upsamplers[0].run(h, None, sdt)
         out = self._out.run(h)

@@ -48,7 +48,9 @@ int b200_linear(const void* A, long long lda, long long a_batch_stride,
                 int act, float alpha,
                 float* chan_stats /* optional [M/rows_per_img][N][2]: per-channel sum / sum of squares of
                                      the stored values, accumulated with atomics (caller zeroes) */,
-                int rows_per_img, void* stream);
+                int rows_per_img,
+                void* out2_f16 /* optional fp16 copy of `out` (same strides) for a following GEMM operand */,
+                void* stream);
 
 /* GEGLU tile width for packed width N (weights/bias rows are interleaved per tile of this width:
  * [value rows of the tile | gate rows of the tile]); 0 = not tileable. */
@@ -71,7 +73,8 @@ int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin,
                      int stride, int Ho, int Wo, int out_mul, int out_oy, int out_ox,
                      const float* bias, const float* rowvec, long long ld_rowvec,
                      const void* residual, void* out, int out_f32, int out_nchw, int act,
-                     float* chan_stats /* optional [NB][Cout][2], see b200_linear */, void* stream);
+                     float* chan_stats /* optional [NB][Cout][2], see b200_linear */,
+                     void* out2_f16 /* optional fp16 NHWC copy of `out` */, void* stream);
 
 /* 3x3 / stride 1 / pad 1 convolution with Cout <= 8 (the `conv_out` layers: unet_2d_condition.py:617-619
  * and the VAE encoder/decoder conv_out): NHWC fp16 in (C % 64 == 0), NCHW fp32 out, input read once.
