@@ -305,6 +305,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         uint32_t* t_out = tab + acc * (2 * BLOCK_N);
         uint32_t* t_res = t_out + BLOCK_N;
+        uint32_t* t_flag = tab + 4 * BLOCK_N + acc * 8;              // per 32-pixel chunk: all rows valid
         for (int pi = et; pi < BLOCK_N; pi += 32 * kEpiWarps) {
           bool ok;
           long long orow;
@@ -321,6 +322,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           t_out[pi] = ok ? (uint32_t)(orow * p.ldo) : 0xFFFFFFFFu;
           t_res[pi] = (uint32_t)(orow * p.ld_res);
+          const unsigned okmask = __ballot_sync(0xffffffffu, ok);   // a warp covers one 32-pixel chunk
+          if ((et & 31) == 0) t_flag[pi >> 5] = (okmask == 0xffffffffu);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");             // table visible to the 8 epilogue warps
         const int ch = n_blk * kBlockM + row_in_tile;
@@ -357,7 +360,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int j = 4 * q4 + e;
-                  rres[j] = (ch_ok && roff[j] != 0xFFFFFFFFu) ? res_b[(size_t)o4[e]] : (OutT)0.f;
+                  rres[j] = (ch_ok && roff[j] != 0xFFFFFFFFu) ? res_b[o4[e]] : (OutT)0.f;
                 }
               }
             }
@@ -375,14 +378,24 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) vals[j] = silu_f(vals[j]);
             }
+            const bool full = t_flag[c >> 5] != 0 && ch_ok;          // interior chunk: no per-element predicates
             if (!(p.debug & 1)) {
+              if (full) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (ch_ok && roff[j] != 0xFFFFFFFFu) out_b[(size_t)roff[j]] = (OutT)vals[j];
-              if (out2_b != nullptr) {
+                for (int j = 0; j < 32; ++j) out_b[roff[j]] = (OutT)vals[j];
+                if (out2_b != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) out2_b[roff[j]] = __float2half_rn(vals[j]);
+                }
+              } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (ch_ok && roff[j] != 0xFFFFFFFFu) out2_b[(size_t)roff[j]] = __float2half_rn(vals[j]);
+                  if (ch_ok && roff[j] != 0xFFFFFFFFu) out_b[roff[j]] = (OutT)vals[j];
+                if (out2_b != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (ch_ok && roff[j] != 0xFFFFFFFFu) out2_b[roff[j]] = __float2half_rn(vals[j]);
+                }
               }
             }
             if (p.chan_stats) {
@@ -508,7 +521,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int rr = 4 * q4 + e;
-                rres[rr] = (col_ok && roff[rr] != 0xFFFFFFFFu) ? res_b[(size_t)o4[e] + col] : (OutT)0.f;
+                rres[rr] = (col_ok && roff[rr] != 0xFFFFFFFFu) ? res_b[o4[e] + col] : (OutT)0.f;
               }
             }
           }
@@ -566,11 +579,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!(p.debug & 1)) {
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr)
-              if (col_ok && roff[rr] != 0xFFFFFFFFu) out_b[(size_t)roff[rr] + col] = (OutT)vals[rr];
+              if (col_ok && roff[rr] != 0xFFFFFFFFu) out_b[roff[rr] + col] = (OutT)vals[rr];
             if (out2_b != nullptr) {
 #pragma unroll
               for (int rr = 0; rr < 32; ++rr)
-                if (col_ok && roff[rr] != 0xFFFFFFFFu) out2_b[(size_t)roff[rr] + col] = __float2half_rn(vals[rr]);
+                if (col_ok && roff[rr] != 0xFFFFFFFFu) out2_b[roff[rr] + col] = __float2half_rn(vals[rr]);
             }
           }
           if (p.chan_stats) {
