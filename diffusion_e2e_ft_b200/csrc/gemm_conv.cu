@@ -167,7 +167,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
                            const float* bias, int bias_row, const void* residual, long long ld_res,
                            long long res_batch_stride, void* out, long long ldo,
                            long long out_batch_stride, int out_f32, int act, float alpha,
-                           float* chan_stats, int rows_per_img, void* out2_f16, void* stream) {
+                           float* chan_stats, int rows_per_img, void* out2_f16, int res_mul, void* stream) {
   B200_CHECK_ARG(A && W && out, "b200_linear: null pointer");
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "b200_linear: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
   B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "b200_linear: lda/ldw must be multiples of 8 elements (16 B)");
@@ -226,7 +226,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   }
   p.out = out; p.ldo = ldo; p.out_batch_stride = out_batch_stride; p.out_f32 = out_f32;
   p.bias = bias; p.bias_row = bias_row;
-  p.residual = residual; p.ld_res = ld_res; p.res_batch_stride = res_batch_stride;
+  p.residual = residual; p.ld_res = ld_res; p.res_batch_stride = res_batch_stride; p.res_mul = res_mul;
   p.act = act; p.alpha = alpha; p.debug = g_debug;
   p.chan_stats = chan_stats; p.rows_per_img = rows_per_img; p.out2 = (__half*)out2_f16;
   p.out_mul = 1;

@@ -31,7 +31,7 @@ constexpr int kAccStages = 2;
 constexpr int kAccStrideCols = 256;
 constexpr int kMaxTaps = 9;
 
-enum EpiAct { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2 };
+enum EpiAct { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_GELU = 3 };
 
 struct GemmParams {
   int M, N, num_k_blocks;
@@ -56,6 +56,7 @@ struct GemmParams {
   int bias_row;
   const float* rowvec;         // per-image vector, indexed [img*ld_rowvec + col]
   long long ld_rowvec;
+  int res_mul;                 // residual operand multiplies (out = act(acc+bias) * residual) instead of adding
   const void* residual;        // same dtype as out
   long long ld_res, res_batch_stride;
   int act;
@@ -370,13 +371,20 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float vals[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) vals[j] = fmaf(__uint_as_float(r[j]), p.alpha, add);
-            if (res_b != nullptr) {
+            if (res_b != nullptr && !p.res_mul) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) vals[j] += (float)rres[j];
             }
             if (p.act == ACT_SILU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) vals[j] = silu_f(vals[j]);
+            } else if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) vals[j] = gelu_erf_f(vals[j]);
+            }
+            if (res_b != nullptr && p.res_mul) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) vals[j] *= (float)rres[j];
             }
             const bool full = t_flag[c >> 5] != 0 && ch_ok;          // interior chunk: no per-element predicates
             if (!(p.debug & 1)) {
@@ -567,13 +575,20 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int rr = 0; rr < 32; ++rr) vals[rr] = fmaf(vals[rr], p.alpha, add);
             }
-            if (res_b != nullptr) {
+            if (res_b != nullptr && !p.res_mul) {
 #pragma unroll
               for (int rr = 0; rr < 32; ++rr) vals[rr] += (float)rres[rr];
             }
             if (p.act == ACT_SILU) {
 #pragma unroll
               for (int rr = 0; rr < 32; ++rr) vals[rr] = silu_f(vals[rr]);
+            } else if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) vals[rr] = gelu_erf_f(vals[rr]);
+            }
+            if (res_b != nullptr && p.res_mul) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) vals[rr] *= (float)rres[rr];
             }
           }
           if (!(p.debug & 1)) {

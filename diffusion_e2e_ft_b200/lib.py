@@ -22,7 +22,7 @@ _SIGS = {
     "b200_debug_set_swap": (None, [c_int]),
     "b200_geglu_block_n": (c_int, [c_int]),
     "b200_linear": (c_int, [_P, _LL, _LL, _P, _LL, _LL, c_int, c_int, c_int, c_int, _P, c_int, _P, _LL, _LL,
-                            _P, _LL, _LL, c_int, c_int, c_float, _P, c_int, _P, _P]),
+                            _P, _LL, _LL, c_int, c_int, c_float, _P, c_int, _P, c_int, _P]),
     "b200_conv2d_nhwc": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int,
                                  POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int,
                                  _P, _P, _LL, _P, _P, c_int, c_int, c_int, _P, _P, _P]),

@@ -238,14 +238,16 @@ class BasicTransformerBlock(nn.Module):
     def _packed(self):
         def build():
             a1, a2 = self.attn1, self.attn2
-            wg, bg = ops.pack_geglu(self.ff.net[0].proj.weight, self.ff.net[0].proj.bias)
+            pw, pb = self.ff.net[0].proj.weight, self.ff.net[0].proj.bias
+            half = pw.shape[0] // 2
             return dict(
                 ln=[(_f32(n.weight), _f32(n.bias)) for n in (self.norm1, self.norm2, self.norm3)],
                 wqkv=_f16(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0)),
                 wo1=_f16(a1.to_out[0].weight), bo1=_f32(a1.to_out[0].bias),
                 wq2=_f16(a2.to_q.weight), wkv2=_f16(torch.cat([a2.to_k.weight, a2.to_v.weight], 0)),
                 wo2=_f16(a2.to_out[0].weight), bo2=_f32(a2.to_out[0].bias),
-                wg=wg, bg=bg, wf=_f16(self.ff.net[2].weight), bf=_f32(self.ff.net[2].bias))
+                wv=_f16(pw[:half]), bv=_f32(pb[:half]), wgt=_f16(pw[half:]), bgt=_f32(pb[half:]),
+                wf=_f16(self.ff.net[2].weight), bf=_f32(self.ff.net[2].bias))
         return self._pk.get(list(self.parameters()), build)
 
     def run(self, h, B, L, ctx16, sdt=F32):
@@ -265,7 +267,10 @@ class BasicTransformerBlock(nn.Module):
         o2 = ops.attention_d64(q2, kv[..., :C], kv[..., C:], heads, scale)
         h = ops.linear(o2.view(B * L, C), pk["wo2"], pk["bo2"], residual=h, out_dtype=sdt)
         n3 = ops.layer_norm(h, *pk["ln"][2])
-        g = ops.linear(n3, pk["wg"], pk["bg"], act=ops.ACT_GEGLU)
+        # GEGLU (attention.py:754-755) as two swapped-operand GEMMs: gate = gelu(x Wg + bg), then
+        # value = (x Wv + bv) * gate in the second epilogue (the fused single-GEMM variant is barrier-bound)
+        gate = ops.linear(n3, pk["wgt"], pk["bgt"], act=ops.ACT_GELU)
+        g = ops.linear(n3, pk["wv"], pk["bv"], residual=gate, res_mul=True)
         return ops.linear(g, pk["wf"], pk["bf"], residual=h, out_dtype=sdt, f16_copy=True)   # proj_out operand
 
 

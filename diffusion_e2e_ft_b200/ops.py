@@ -10,7 +10,7 @@ import torch
 
 from . import lib as _lib
 
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU = 0, 1, 2, 3
 F16, F32 = torch.float16, torch.float32
 
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]        # pad=1
@@ -133,7 +133,7 @@ def _new_stats(nb, c, device):
 
 @_timed("gemm_linear")
 def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE, alpha=1.0,
-           bias_row=False, stats_rows_per_img=0, f16_copy=False):
+           bias_row=False, stats_rows_per_img=0, f16_copy=False, res_mul=False):
     """`stats_rows_per_img` > 0: also accumulate per-(image, channel) sum / sum-of-squares of the output
     (attached to the result as `._cs`) for a following GroupNorm.  `f16_copy`: an fp32 output also gets an
     fp16 twin (`._h16`) written by the same epilogue, so a following GEMM needs no cast pass."""
@@ -167,7 +167,7 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
         _p(residual), residual.stride(-2) if residual is not None else 0,
         (residual.stride(0) if (residual is not None and batched) else 0),
         _p(out), out.stride(-2), out.stride(0) if batched else 0, int(out.dtype == F32),
-        act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _p(h16), _stream())
+        act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _p(h16), int(res_mul), _stream())
     _lib.check(rc, "b200_linear")
     STATS.add("linear", 2 * B * M * N * K)
     if ev is not None:

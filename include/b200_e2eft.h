@@ -31,6 +31,7 @@ int b200_abi_version(void);
 #define B200_ACT_NONE 0
 #define B200_ACT_SILU 1
 #define B200_ACT_GEGLU 2 /* W rows pre-interleaved per tile: [value half | gate half] */
+#define B200_ACT_GELU 3  /* erf GELU */
 
 /* out[b][m][n] = act( alpha * sum_k A[b][m][k] * W[(b)][n][k] + bias + residual[b][m][n] )
  * tcgen05 GEMM, fp16 operands (K contiguous), fp32 accumulate in TMEM.
@@ -50,6 +51,7 @@ int b200_linear(const void* A, long long lda, long long a_batch_stride,
                                      the stored values, accumulated with atomics (caller zeroes) */,
                 int rows_per_img,
                 void* out2_f16 /* optional fp16 copy of `out` (same strides) for a following GEMM operand */,
+                int res_mul /* 1: out = act(alpha*acc + bias) * residual (GEGLU as gate GEMM + value GEMM) */,
                 void* stream);
 
 /* GEGLU tile width for packed width N (weights/bias rows are interleaved per tile of this width:

@@ -56,6 +56,18 @@ def check_linear(M=300, N=320, K=320, bias=True, residual=False, out_f32=False, 
     return err, tol
 
 
+def check_geglu_two_gemm(M=300, C=320, seed=17):
+    """GEGLU as gate GEMM (erf-GELU epilogue) + value GEMM with a multiplicative residual operand."""
+    a = _rand(M, C, seed=seed)
+    w = _rand(8 * C, C, seed=seed + 1, scale=1 / math.sqrt(C))
+    b = _rand(8 * C, seed=seed + 2, dtype=torch.float32)
+    gate = ops.linear(a, w[4 * C:].contiguous(), b[4 * C:].contiguous(), act=ops.ACT_GELU)
+    out = ops.linear(a, w[:4 * C].contiguous(), b[:4 * C].contiguous(), residual=gate, res_mul=True)
+    torch.cuda.synchronize()
+    h, g = (a.float() @ w.float().t() + b).chunk(2, dim=-1)
+    return rel_l2(out, h * F.gelu(g)), 1.5e-3
+
+
 def check_linear_bias_row(seed=5):
     """D[m,n] = W[m,:]·h[n,:] + bias[m]  (V^T projection of the VAE attention)."""
     M, N, K = 512, 700, 512
@@ -304,6 +316,8 @@ CHECKS = {
     "linear_geglu_small": lambda: check_linear(M=100, N=512, K=64, act=ops.ACT_GEGLU),
     "linear_batched": lambda: check_linear(M=200, N=300 // 4 * 4 + 4, K=512, batch=3, bias=False),
     "linear_bias_row": check_linear_bias_row,
+    "geglu_two_gemm": check_geglu_two_gemm,
+    "geglu_two_gemm_64": lambda: check_geglu_two_gemm(M=100, C=64),
     "linear_unaligned_ldo": lambda: check_linear(M=130, N=700, K=128, residual=True, seed=7),
     "conv_s1": lambda: check_conv(),
     "conv_s1_96": lambda: check_conv(NB=1, H=96, W=96, Cin=64, Cout=320),
