@@ -6,27 +6,35 @@
 
 namespace b200 {
 
-// out[pixel][tap*C + c] (fp16, row length Kpad, zero padded), x NCHW.  One thread per output
-// element pair; consecutive threads walk the K (tap,c) dimension -> coalesced 2-byte stores are
-// merged by the row-major layout; reads are strided but the whole input is tiny (C <= 8).
-template <typename T>
+// out[pixel][tap*C + c] (fp16, row length Kpad, zero padded), x NCHW.  One thread per pixel: it gathers the
+// 9*C (<= 72) neighbours (L1/L2-served: neighbouring threads share them) and writes its whole patch row with
+// 16-byte stores, so the 64-128 byte rows leave as full sectors.
+template <typename T, int KPAD>
 __global__ void im2col3x3_kernel(const T* __restrict__ x, int NB, int C, int H, int W,
-                                 __half* __restrict__ out, int Kpad) {
-  const long long total = (long long)NB * H * W * Kpad;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % Kpad);
-    const long long pix = i / Kpad;
-    float v = 0.f;
-    if (k < 9 * C) {
-      const int tap = k / C, c = k - tap * C;
-      const int w = (int)(pix % W);
-      const int h = (int)((pix / W) % H);
-      const int n = (int)(pix / ((long long)W * H));
+                                 __half* __restrict__ out) {
+  const long long total = (long long)NB * H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    constexpr int CC = KPAD == 32 ? 3 : (KPAD == 40 ? 4 : 8);       // compile-time channel count: row[] stays in registers
+    __align__(16) __half row[KPAD];
+#pragma unroll
+    for (int k = 0; k < KPAD; ++k) row[k] = __float2half_rn(0.f);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
       const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = (float)x[(((long long)n * C + c) * H + hh) * W + ww];
+      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+      for (int c = 0; c < CC; ++c)
+        row[tap * CC + c] = ok ? __float2half_rn((float)x[(((long long)n * CC + c) * H + hh) * W + ww])
+                               : __float2half_rn(0.f);
     }
-    out[i] = __float2half_rn(v);
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * KPAD);
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int v = 0; v < KPAD / 8; ++v) dst[v] = src[v];
   }
 }
 
@@ -162,12 +170,18 @@ extern "C" int b200_im2col3x3_nchw(const void* x, int x_f32, int NB, int C, int 
                                    int Kpad, void* stream) {
   B200_CHECK_ARG(x && out && NB > 0 && C > 0 && H > 0 && W > 0, "b200_im2col3x3_nchw: bad arguments");
   B200_CHECK_ARG(Kpad >= 9 * C && Kpad % 8 == 0, "b200_im2col3x3_nchw: Kpad=%d must be >= 9*C and %%8==0", Kpad);
-  const long long total = (long long)NB * H * W * Kpad;
+  B200_CHECK_ARG((Kpad == 32 && C == 3) || (Kpad == 40 && C == 4) || (Kpad == 72 && C == 8),
+                 "b200_im2col3x3_nchw: (C=%d, Kpad=%d) unsupported: C must be 3, 4 or 8 with Kpad = round_up(9C, 8)", C, Kpad);
+  const long long total = (long long)NB * H * W;
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_f32)
-    im2col3x3_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, NB, C, H, W, (__half*)out, Kpad);
-  else
-    im2col3x3_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>((const __half*)x, NB, C, H, W, (__half*)out, Kpad);
+  const int g = grid_for(total, 128);
+#define B200_IM2COL(T, K) im2col3x3_kernel<T, K><<<g, 128, 0, st>>>((const T*)x, NB, C, H, W, (__half*)out)
+  if (x_f32) {
+    if (Kpad == 32) B200_IM2COL(float, 32); else if (Kpad == 40) B200_IM2COL(float, 40); else B200_IM2COL(float, 72);
+  } else {
+    if (Kpad == 32) B200_IM2COL(__half, 32); else if (Kpad == 40) B200_IM2COL(__half, 40); else B200_IM2COL(__half, 72);
+  }
+#undef B200_IM2COL
   B200_CHECK_LAUNCH("im2col3x3_kernel");
   return 0;
 }

@@ -156,14 +156,14 @@ __global__ void gn_apply_kernel(const T* __restrict__ x1, int C1, const T* __res
   const int p1 = min(HW, p0 + pix_per_cta);
   __half* yb = y + (long long)n * HW * C + c0;
   __half* rb = raw ? raw + (long long)n * HW * C + c0 : nullptr;
-  // 4 pixels per iteration: four independent 16-byte loads in flight per thread (latency-bound otherwise)
+  // 8 pixels per iteration: eight independent 16/32-byte loads in flight per thread (latency-bound otherwise)
   int p = p0 + r;
-  for (; p + 3 * rpb < p1; p += 4 * rpb) {
-    float f[4][8];
+  for (; p + 7 * rpb < p1; p += 8 * rpb) {
+    float f[8][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load8(base + (long long)(p + u * rpb) * ld, f[u]);
+    for (int u = 0; u < 8; ++u) load8(base + (long long)(p + u * rpb) * ld, f[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
