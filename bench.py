@@ -355,10 +355,14 @@ def run_engine(args):
         conv_tf = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         ms_eager = eager_ms / rsteps
         peak = peaks["tflops_sustained"]
-        traffic = None
+        traffic, traffic_of = None, None
         tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_of = (f"one ncu --set full capture of {tj.get('kernel')} on {tj.get('shape')}: "
+                          f"{tj.get('algorithmic_flops', 0) / 1e12:.3f} TFLOP, algorithmic bytes >= "
+                          f"{tj.get('algorithmic_bytes_min', 0) / 1e9:.3f} GB ({tj.get('source')})")
         out = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -379,7 +383,7 @@ def run_engine(args):
             "breakdown_ms_eager_step": {k: round(v, 2) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
             "roofline": {"kernel": "gemm_conv_kernel (implicit-GEMM conv3x3, tcgen05+TMA)", "bound": "tensor",
                          "achieved": conv_tf, "peak": peak, "unit": "TFLOP/s", "frac": conv_tf / peak,
-                         "traffic": traffic, "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "traffic": traffic, "traffic_of": traffic_of, "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_timed": n_conv, "avg_launch_ms": conv_ms / max(1, n_conv),
                          "share_of_step": (conv_ms / rsteps) / (ms / args.steps),
                          "timed_in": f"{rsteps} eagerly launched steps of the same workload ({ms_eager:.1f} ms/step eager)"},
