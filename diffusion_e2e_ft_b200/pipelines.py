@@ -230,6 +230,14 @@ class MarigoldPipeline(PipelineBase):
                      normals=False, generator=None):
         device = self.device
         rgb_in = rgb_in.to(device)
+        # the kernels index each tensor with 32-bit element offsets: split batches whose largest activation
+        # (256 channels at full resolution in the VAE decoder) would exceed 2^32 elements
+        B, _, H, W = rgb_in.shape
+        max_b = max(1, (2 ** 32 - 1) // (256 * H * W))
+        if B > max_b:
+            return torch.cat([self.single_infer(rgb_in[i:i + max_b], num_inference_steps, show_pbar, noise=noise,
+                                                normals=normals, generator=generator)
+                              for i in range(0, B, max_b)], dim=0)
         if (self.use_cuda_graph and noise == "zeros" and num_inference_steps == 1 and rgb_in.is_cuda
                 and not torch.cuda.is_current_stream_capturing()):
             key = ("marigold", tuple(rgb_in.shape), rgb_in.dtype, bool(normals))
