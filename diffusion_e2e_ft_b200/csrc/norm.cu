@@ -317,8 +317,8 @@ static int gn_common_check(const char* fn, const void* x1, int C1, const void* x
 }
 
 static int gn_chunks(int NB, int HW, int rows_per_pass) {
-  // ~4 CTAs per SM across the batch, at least rows_per_pass pixels per CTA
-  int target = (sm_count() * 4 + NB - 1) / NB;
+  // ~8 CTAs per SM across the batch (2048 threads/SM: maximum bytes in flight), at least rows_per_pass pixels per CTA
+  int target = (sm_count() * 8 + NB - 1) / NB;
   int ppc = (HW + target - 1) / target;
   if (ppc < rows_per_pass * 4) ppc = rows_per_pass * 4;
   return ppc;
