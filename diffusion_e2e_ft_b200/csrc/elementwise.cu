@@ -116,16 +116,20 @@ __global__ void decode_post_kernel(const float* __restrict__ x, long long HW, in
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW;
        p += (long long)gridDim.x * blockDim.x) {
     const float a = xb[p], b = xb[HW + p], c = xb[2 * HW + p];
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
       float m = (a + b + c) / 3.0f;
       m = fminf(fmaxf(m, -1.0f), 1.0f);
-      out[(long long)n * HW + p] = (m + 1.0f) / 2.0f;
+      out[(long long)n * HW + p] = mode == 0 ? (m + 1.0f) / 2.0f : m;     // mode 2: training (train.py:533-534)
     } else {
       const float inv = sign / (sqrtf(a * a + b * b + c * c) + 1e-5f);
       float* ob = out + (long long)n * 3 * HW;
-      ob[p] = a * inv;
-      ob[HW + p] = b * inv;
-      ob[2 * HW + p] = c * inv;
+      float v0 = a * inv, v1 = b * inv, v2 = c * inv;
+      if (mode == 3) {                                                     // training: clamp (train.py:539)
+        v0 = fminf(fmaxf(v0, -1.f), 1.f); v1 = fminf(fmaxf(v1, -1.f), 1.f); v2 = fminf(fmaxf(v2, -1.f), 1.f);
+      }
+      ob[p] = v0;
+      ob[HW + p] = v1;
+      ob[2 * HW + p] = v2;
     }
   }
 }
@@ -222,7 +226,7 @@ extern "C" int b200_pointwise_nchw(const float* in1, float a1, const float* in2,
 
 extern "C" int b200_decode_post(const float* x, int NB, long long HW, int mode, float sign, float* out,
                                 void* stream) {
-  B200_CHECK_ARG(x && out && NB > 0 && HW > 0 && (mode == 0 || mode == 1), "b200_decode_post: bad arguments");
+  B200_CHECK_ARG(x && out && NB > 0 && HW > 0 && mode >= 0 && mode <= 3, "b200_decode_post: bad arguments");
   dim3 grid(grid_for(HW, 256), NB);
   decode_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, HW, mode, sign, out);
   B200_CHECK_LAUNCH("decode_post_kernel");

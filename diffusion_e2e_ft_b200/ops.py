@@ -384,14 +384,44 @@ def pointwise_nchw(in1, a1, wm, bias, in2=None, a2=0.0, cin=None):
 
 
 @_timed("misc")
-def decode_post(x, normals=False, sign=1.0):
+def decode_post(x, normals=False, sign=1.0, training=False):
+    """`training`: the train.py:532-540 variants (no (x+1)/2 map for depth; clamp after normalising)."""
     _need_cuda(x)
     assert x.dtype == F32 and x.is_contiguous() and x.shape[1] == 3
     NB, _, H, W = x.shape
     out = torch.empty((NB, 3 if normals else 1, H, W), dtype=F32, device=x.device)
-    _ck(_lib.load().b200_decode_post(_p(x), NB, H * W, int(normals), float(sign), _p(out), _stream()),
-               "b200_decode_post")
+    mode = int(normals) + (2 if training else 0)
+    _ck(_lib.load().b200_decode_post(_p(x), NB, H * W, mode, float(sign), _p(out), _stream()),
+        "b200_decode_post")
     return out
+
+
+@_timed("loss")
+def ssi_loss(pred, target, mask):
+    """ScaleAndShiftInvariantLoss forward (training/util/loss.py:13-47): pred/target [B,1,H,W] fp32, mask bool."""
+    _need_cuda(pred, target, mask)
+    B = pred.shape[0]
+    hw = pred.numel() // B
+    p, t = pred.float().contiguous(), target.float().contiguous()
+    m = mask.reshape(B, -1).to(torch.uint8).contiguous()
+    ws = torch.zeros(5 * B + 2, dtype=torch.float64, device=pred.device)
+    out = torch.empty(1, dtype=F32, device=pred.device)
+    _ck(_lib.load().b200_ssi_loss(_p(p), _p(t), _p(m), B, hw, _p(ws), _p(out), _stream()), "b200_ssi_loss")
+    return out[0]
+
+
+@_timed("loss")
+def angular_loss(pred, target, mask):
+    """AngularLoss forward (training/util/loss.py:51-67): pred/target [B,3,H,W] fp32, mask [B,1,H,W] bool."""
+    _need_cuda(pred, target, mask)
+    B = pred.shape[0]
+    hw = pred.numel() // (3 * B)
+    p, t = pred.float().contiguous(), target.float().contiguous()
+    m = mask.reshape(B, -1).to(torch.uint8).contiguous()
+    ws = torch.zeros(2, dtype=torch.float64, device=pred.device)
+    out = torch.empty(1, dtype=F32, device=pred.device)
+    _ck(_lib.load().b200_angular_loss(_p(p), _p(t), _p(m), B, hw, _p(ws), _p(out), _stream()), "b200_angular_loss")
+    return out[0]
 
 
 @_timed("cast")

@@ -1,0 +1,38 @@
+"""Forward half of the E2E fine-tuning step (training/train.py:469-556) on the engine.
+
+    rgb -> VAE.encode * scaling -> UNet(t = T-1, zeros noise, ctx[B,77,1024]) -> x0 (v-prediction)
+        -> / scaling -> VAE.decode -> depth: mean_c, clamp | normals: normalise, clamp -> SSI / angular loss
+
+Everything runs in libb200_e2eft.so kernels (incl. the losses).  The BACKWARD (conv dgrad/wgrad, attention
+backward, GN/LN backward, AdamW, NCCL gradient all-reduce) is not implemented in round 1: this module is
+inference-mode only and exists so the loss value of a training micro-step can be checked against the oracle.
+"""
+import math
+
+import torch
+
+from . import ops
+
+
+@torch.no_grad()
+def e2e_ft_forward(unet, vae, scheduler, rgb, ground_truth, val_mask, empty_encoding, modality="depth"):
+    """Returns (loss [0-d fp32 tensor], current_estimate).  rgb [B,3,H,W] in [-1,1]; ground_truth [B,1,H,W]
+    metric depth or [B,3,H,W] normals; val_mask [B,1,H,W] bool; empty_encoding [1,77,1024]."""
+    B = rgb.shape[0]
+    rgb_latents = vae.encode_scaled_mean(rgb)                                   # train.py:473-474
+    T = scheduler.config["num_train_timesteps"]
+    t = T - 1                                                                   # :480-481
+    noisy = torch.zeros_like(rgb_latents)                                       # :484-485 (noise_type zeros)
+    ctx = empty_encoding.to(rgb.device).repeat(B, 1, 1)
+    model_pred = unet(torch.cat((rgb_latents, noisy), dim=1), t, ctx, return_dict=False)[0]     # :494-500
+    a_t = float(scheduler.alphas_cumprod[t])
+    assert scheduler.config["prediction_type"] == "v_prediction"
+    dec = vae.decode_from_prediction(model_pred, -math.sqrt(1.0 - a_t))         # :509-529 (x_t = 0)
+    est = ops.decode_post(dec.float().contiguous(), normals=(modality == "normals"), training=True)   # :532-540
+    if modality == "depth":
+        loss = ops.ssi_loss(est, ground_truth, val_mask)                        # :545
+    elif modality == "normals":
+        loss = ops.angular_loss(est, ground_truth, val_mask)                    # :549
+    else:
+        raise ValueError(f"Unknown modality {modality}")
+    return loss, est

@@ -150,9 +150,19 @@ int b200_pointwise_nchw(const float* in1, float a1, const float* in2, float a2, 
                         float* out, void* stream);
 
 /* Decode post-ops on NCHW fp32 [B][3][HW]: mode 0 = depth: (clip(mean_c, -1, 1)+1)/2 -> [B][1][HW];
- * mode 1 = normals: x/(||x||_2+1e-5) * sign -> [B][3][HW].  marigold_pipeline.py:467-478. */
+ * mode 1 = normals: x/(||x||_2+1e-5) * sign -> [B][3][HW] (marigold_pipeline.py:467-478);
+ * mode 2 / 3 = the training variants: clip(mean_c) without the affine map / normalised then clamped
+ * (training/train.py:532-540). */
 int b200_decode_post(const float* x, int NB, long long HW, int mode, float sign, float* out,
                      void* stream);
+
+/* Task losses of the E2E fine-tuning step, forward only (training/util/loss.py:13-67, training/train.py:542-556).
+ * pred/target NCHW fp32 ([B][1][HW] depth, [B][3][HW] normals), mask [B][HW] bytes, workspace: zeroed doubles
+ * (5*B + 2 for SSI, 2 for angular), out: one float (mean over masked pixels; nan for an empty mask). */
+int b200_ssi_loss(const float* pred, const float* target, const unsigned char* mask, int B, long long HW,
+                  double* workspace, float* out, void* stream);
+int b200_angular_loss(const float* pred, const float* target, const unsigned char* mask, int B, long long HW,
+                      double* workspace, float* out, void* stream);
 
 /* fp32 <-> fp16 casts / layout helpers used at module boundaries. */
 int b200_cast_f32_to_f16(const float* x, void* y, long long n, void* stream);

@@ -151,3 +151,29 @@ def run_full_size(device="cuda:0", res=768, batch=1, stream_dtype=torch.float32)
     two = pipe.single_infer(torch.cat([rgb[:1], rgb[:1]]), 1, False, noise="zeros")
     out["batch_consistency"] = max(rel_l2(two[0:1], got[0:1]), rel_l2(two[1:2], got[0:1]))
     return out
+
+
+@torch.no_grad()
+def run_training_forward_tiny(device="cuda:0", modality="depth"):
+    """Forward half of training/train.py:469-556 (bs=2, ctx 77 tokens) on the engine vs the oracle."""
+    from diffusion_e2e_ft_b200.training import e2e_ft_forward
+    unet_ref, vae_ref = MG.build_tiny()
+    unet, vae = engine_from_oracle(unet_ref, vae_ref, device)
+    g = torch.Generator().manual_seed(13)
+    rgb = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    ctx = torch.randn(1, 77, 128, generator=g) * 0.5
+    mask = torch.rand(2, 1, 64, 64, generator=g) > 0.2
+    sched_o = OP.DDIMOneStep()
+    lat = OP.encode_rgb(vae_ref, rgb)
+    v = unet_ref(torch.cat([lat, torch.zeros_like(lat)], 1), 999, ctx.repeat(2, 1, 1)).sample
+    dec = OP.decode_latent(vae_ref, sched_o.pred_original_sample(v, 999, torch.zeros_like(lat)))
+    if modality == "depth":
+        gt = torch.rand(2, 1, 64, 64, generator=g) * 9.9 + 0.1
+        want = OP.ssi_loss(dec.mean(1, keepdim=True).clamp(-1, 1), gt, mask)
+    else:
+        gt = torch.nn.functional.normalize(torch.randn(2, 3, 64, 64, generator=g), dim=1)
+        est = dec / (dec.norm(dim=1, keepdim=True) + 1e-5)
+        want = OP.angular_loss(est.clamp(-1, 1), gt, mask)
+    got, _ = e2e_ft_forward(unet, vae, DDIMScheduler(), rgb.to(device), gt.to(device), mask.to(device), ctx.to(device),
+                            modality)
+    return dict(loss_engine=got.item(), loss_oracle=want.item(), rel_err=abs(got.item() - want.item()) / abs(want.item()))

@@ -252,6 +252,25 @@ def check_attention(B=2, heads=5, Lq=576, Lk=None, joint=False, gain=3.0, seed=0
 
 
 # ----------------------------------------------------------------------------------- elementwise
+def check_losses(seed=51):
+    """SSI / angular loss kernels against the oracle restatement of training/util/loss.py."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import pipeline as OP
+    pred = _rand(3, 1, 40, 56, seed=seed, dtype=torch.float32).clamp(-1, 1)
+    gt = (_rand(3, 1, 40, 56, seed=seed + 1, dtype=torch.float32).abs() * 3 + 0.1)
+    mask = _rand(3, 1, 40, 56, seed=seed + 2, dtype=torch.float32) > -0.5
+    e1 = abs(ops.ssi_loss(pred, gt, mask).item() - OP.ssi_loss(pred.cpu(), gt.cpu(), mask.cpu()).item())
+    n1 = F.normalize(_rand(3, 3, 40, 56, seed=seed + 3, dtype=torch.float32), dim=1)
+    n2 = F.normalize(_rand(3, 3, 40, 56, seed=seed + 4, dtype=torch.float32), dim=1)
+    e2 = abs(ops.angular_loss(n1, n2, mask).item() - OP.angular_loss(n1.cpu(), n2.cpu(), mask.cpu()).item())
+    d = _rand(2, 3, 9, 7, seed=seed + 5, dtype=torch.float32)
+    e3 = rel_l2(ops.decode_post(d, training=True), d.mean(1, keepdim=True).clamp(-1, 1))
+    e4 = rel_l2(ops.decode_post(d, normals=True, training=True), (d / (d.norm(dim=1, keepdim=True) + 1e-5)).clamp(-1, 1))
+    torch.cuda.synchronize()
+    return max(e1, e2, e3, e4), 2e-5
+
+
 def check_upsample(in_f32=False, out_hw=None):
     dt = torch.float32 if in_f32 else torch.float16
     x = _rand(2, 7, 9, 64, dtype=dt)
@@ -366,4 +385,5 @@ CHECKS = {
     "upsample_size_f32": lambda: check_upsample(True, (15, 20)),
     "timestep_embedding": check_timestep_embedding,
     "pointwise_post": check_pointwise_and_post,
+    "losses_ssi_angular": check_losses,
 }

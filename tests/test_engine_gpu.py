@@ -72,3 +72,12 @@ def test_full_size_768_against_fp32_oracle_on_gpu():
     assert 0.0 <= r["depth_min"] and r["depth_max"] <= 1.0, r
     assert r["normals_norm_err"] <= 2e-3, r
     assert r["batch_consistency"] <= 1e-3, r
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("modality", ["depth", "normals"])
+def test_training_step_forward_loss_matches_oracle(modality):
+    """training/train.py:469-556 forward (encode -> UNet(ctx 77) -> x0 -> decode -> post-op -> loss)."""
+    r = EC.run_training_forward_tiny(modality=modality)
+    print(r)
+    assert r["rel_err"] <= 3e-3, r
