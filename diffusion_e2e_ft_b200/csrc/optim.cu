@@ -1,0 +1,71 @@
+// Optimizer-side kernels of the fine-tuning step over FLAT fp32 buffers (all UNet parameters / gradients /
+// moments live in one contiguous allocation each): squared-gradient-norm reduction for
+// `clip_grad_norm_` and a fused clip + AdamW update.  Reference: training/train.py:346-353 (AdamW:
+// lr 3e-5, betas (0.9, 0.999), weight_decay 1e-2, eps 1e-8) and :564-566 (clip to max_grad_norm, step).
+// HBM-bound: 16 B read + 12 B written per parameter.
+#include "common.cuh"
+#include "../../include/b200_e2eft.h"
+
+namespace b200 {
+
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  double acc = 0;
+  const long long n4 = n / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x4[i];
+    acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += (double)x[i] * x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// torch.optim.AdamW (decoupled weight decay, bias-corrected), gradient pre-scaled by the clip coefficient
+// min(1, max_norm / (||g|| + 1e-6)) read from the device (no host sync between norm and step).
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                             float wd, float bc1, float bc2, const double* __restrict__ gnorm_sq, float max_norm) {
+  float clip = 1.0f;
+  if (gnorm_sq != nullptr && max_norm > 0.f) {
+    const float nrm = (float)sqrt(*gnorm_sq);
+    clip = fminf(1.0f, max_norm / (nrm + 1e-6f));
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * clip;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_sumsq(const float* x, long long n, double* out, void* stream) {
+  B200_CHECK_ARG(x && out && n > 0 && ((uintptr_t)x & 15) == 0, "b200_sumsq: bad arguments (x must be 16-byte aligned)");
+  long long g = (n / 4 + 255) / 256;
+  long long cap = (long long)sm_count() * 8;
+  sumsq_kernel<<<(unsigned)(g < 1 ? 1 : (g > cap ? cap : g)), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  B200_CHECK_LAUNCH("sumsq_kernel");
+  return 0;
+}
+
+extern "C" int b200_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                               const double* grad_norm_sq, float max_grad_norm, void* stream) {
+  B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "b200_adamw_step: bad arguments");
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  long long g = (n + 255) / 256;
+  long long cap = (long long)sm_count() * 8;
+  adamw_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_norm_sq, max_grad_norm);
+  B200_CHECK_LAUNCH("adamw_kernel");
+  return 0;
+}

@@ -424,6 +424,28 @@ def angular_loss(pred, target, mask):
     return out[0]
 
 
+@_timed("optim")
+def grad_norm_sq(flat_grad):
+    """Sum of squares of a flat fp32 gradient buffer -> 0-d float64 device tensor (no host sync)."""
+    _need_cuda(flat_grad)
+    assert flat_grad.dtype == F32 and flat_grad.is_contiguous()
+    out = torch.zeros(1, dtype=torch.float64, device=flat_grad.device)
+    _ck(_lib.load().b200_sumsq(_p(flat_grad), flat_grad.numel(), _p(out), _stream()), "b200_sumsq")
+    return out
+
+
+@_timed("optim")
+def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+               grad_norm_sq_t=None, max_grad_norm=0.0):
+    """Fused clip_grad_norm_ + AdamW on flat fp32 buffers, in place (training/train.py:346-353,564-566)."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == F32 and t.is_contiguous() and t.numel() == param.numel()
+    _ck(_lib.load().b200_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
+                                    float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                    _p(grad_norm_sq_t), float(max_grad_norm), _stream()), "b200_adamw_step")
+
+
 @_timed("cast")
 def cast_f16(x):
     h = getattr(x, "_h16", None)

@@ -36,3 +36,26 @@ def e2e_ft_forward(unet, vae, scheduler, rgb, ground_truth, val_mask, empty_enco
     else:
         raise ValueError(f"Unknown modality {modality}")
     return loss, est
+
+
+def allreduce_mean_(flat_grad, group=None):
+    """DDP gradient exchange of the fine-tuning step (training/train.py:470,563 via accelerate): one all-reduce
+    of the flat gradient buffer over the data-parallel ranks, averaged.  NCCL over NVLink on the GPU box, gloo
+    in the CPU tests.  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat_grad
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    flat_grad.div_(dist.get_world_size(group))
+    return flat_grad
+
+
+def optimizer_step_(flat_param, flat_grad, exp_avg, exp_avg_sq, step, lr=3e-5, weight_decay=1e-2, max_grad_norm=1.0,
+                    group=None):
+    """all-reduce -> clip_grad_norm_(max_grad_norm) -> AdamW, fused on the device without host syncs
+    (training/train.py:563-566 with the recipe of training/scripts/train_marigold_e2e_ft_depth.sh)."""
+    allreduce_mean_(flat_grad, group)
+    nsq = ops.grad_norm_sq(flat_grad)
+    ops.adamw_step(flat_param, flat_grad, exp_avg, exp_avg_sq, step, lr=lr, weight_decay=weight_decay,
+                   grad_norm_sq_t=nsq, max_grad_norm=max_grad_norm)
+    return nsq

@@ -164,6 +164,15 @@ int b200_ssi_loss(const float* pred, const float* target, const unsigned char* m
 int b200_angular_loss(const float* pred, const float* target, const unsigned char* mask, int B, long long HW,
                       double* workspace, float* out, void* stream);
 
+/* Optimizer side of the fine-tuning step on flat fp32 buffers (training/train.py:346-353,564-566):
+ * sum of squares (gradient norm; `out` is a zeroed double accumulated with atomics) and a fused
+ * clip_grad_norm_ + torch.optim.AdamW update (decoupled weight decay, bias correction by `step` >= 1).
+ * grad_norm_sq (device, may be NULL) and max_grad_norm give the clip coefficient without a host sync. */
+int b200_sumsq(const float* x, long long n, double* out, void* stream);
+int b200_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    const double* grad_norm_sq, float max_grad_norm, void* stream);
+
 /* fp32 <-> fp16 casts / layout helpers used at module boundaries. */
 int b200_cast_f32_to_f16(const float* x, void* y, long long n, void* stream);
 int b200_nhwc_to_nchw_f32(const void* x, int in_f32, int NB, int C, long long HW, float* y, void* stream);

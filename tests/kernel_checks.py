@@ -271,6 +271,26 @@ def check_losses(seed=51):
     return max(e1, e2, e3, e4), 2e-5
 
 
+def check_adamw(seed=61, n=100003):
+    """Fused clip + AdamW over a flat buffer vs torch.optim.AdamW + clip_grad_norm_ (training/train.py:346-353,564-566)."""
+    p0 = _rand(n, seed=seed, dtype=torch.float32)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=3e-3, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    worst = 0.0
+    for step in range(1, 4):
+        g = _rand(n, seed=seed + step, dtype=torch.float32) * (3.0 if step == 2 else 0.001)
+        ref_p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        nsq = ops.grad_norm_sq(g)
+        ops.adamw_step(p, g, m, v, step, lr=3e-3, grad_norm_sq_t=nsq, max_grad_norm=1.0)
+        torch.cuda.synchronize()
+        worst = max(worst, rel_l2(p, ref_p.data), abs(nsq.item() - float((g.double() ** 2).sum())) / nsq.item())
+    return worst, 2e-6
+
+
 def check_upsample(in_f32=False, out_hw=None):
     dt = torch.float32 if in_f32 else torch.float16
     x = _rand(2, 7, 9, 64, dtype=dt)
@@ -386,4 +406,5 @@ CHECKS = {
     "timestep_embedding": check_timestep_embedding,
     "pointwise_post": check_pointwise_and_post,
     "losses_ssi_angular": check_losses,
+    "adamw_clip_fused": check_adamw,
 }

@@ -122,3 +122,22 @@ print("OK", lo, hi)
     outs = [p.communicate(timeout=180) for p in ps]
     assert all(p.returncode == 0 for p in ps), outs
     assert sorted(o[0].split()[1:] for o in outs) == [["0", "8"], ["8", "16"]]
+
+
+def test_two_rank_gloo_gradient_allreduce():
+    """training.allreduce_mean_: the only collective of the training path (DDP gradient average)."""
+    code = r'''
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from diffusion_e2e_ft_b200.training import allreduce_mean_
+r = int(sys.argv[1])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29583", rank=r, world_size=2)
+g = torch.full((1000,), float(r + 1))
+allreduce_mean_(g)
+assert torch.allclose(g, torch.full((1000,), 1.5)), g[:4]
+print("OK")
+''' % ROOT
+    ps = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+          for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in ps]
+    assert all(p.returncode == 0 for p in ps), outs
