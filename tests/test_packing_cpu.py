@@ -78,3 +78,55 @@ def test_small_cout_fragment_packing_roundtrip():
         c = chunk * 64 + ks * 16 + k
         assert abs(wq[chunk, tap, ks, n, k] - w[n, c, tap // 3, tap % 3].half().float()) < 1e-6
     assert wq[:, :, :, 3:].abs().max() == 0               # padded output channels are zero
+
+
+# ---------------------------------------------------------------------------------- backward packing
+def _grad_input(fn, x, dy):
+    x = x.clone().requires_grad_(True)
+    (fn(x) * dy).sum().backward()
+    return x.grad
+
+
+def test_conv_dgrad_stride1_is_a_tap_conv_with_flipped_weights():
+    from diffusion_e2e_ft_b200.backward_packing import pack_conv_dgrad_s1
+    g = torch.Generator().manual_seed(5)
+    w = (torch.randn(6, 8, 3, 3, generator=g) * 0.3).half().float()
+    x = torch.randn(2, 8, 7, 9, generator=g)
+    dy = torch.randn(2, 6, 7, 9, generator=g).half().float()
+    want = _grad_input(lambda t: F.conv2d(t, w, padding=1), x, dy).permute(0, 2, 3, 1)
+    wp, taps = pack_conv_dgrad_s1(w)
+    got = tap_conv_reference(dy.permute(0, 2, 3, 1), wp, 8, taps)
+    assert torch.allclose(got, want, atol=2e-2), (got - want).abs().max()
+
+
+def test_conv_dgrad_stride2_four_phase():
+    from diffusion_e2e_ft_b200.backward_packing import pack_conv_dgrad_s2
+    g = torch.Generator().manual_seed(6)
+    w = (torch.randn(5, 8, 3, 3, generator=g) * 0.3).half().float()
+    for pad_lo, fwd in ((1, lambda t: F.conv2d(t, w, stride=2, padding=1)),
+                        (0, lambda t: F.conv2d(F.pad(t, (0, 1, 0, 1)), w, stride=2))):
+        x = torch.randn(2, 8, 10, 12, generator=g)
+        y = fwd(x)
+        dy = torch.randn(y.shape, generator=g).half().float()
+        want = _grad_input(fwd, x, dy).permute(0, 2, 3, 1)
+        got = torch.zeros_like(want)
+        for (py, px), (wp, taps) in pack_conv_dgrad_s2(w, pad_lo).items():
+            tap_conv_reference(dy.permute(0, 2, 3, 1), wp, 8, taps, out_hw=(5, 6), out_mul=2, out_off=(py, px), out=got)
+        assert torch.allclose(got, want, atol=2e-2), (pad_lo, (got - want).abs().max())
+
+
+def test_upsample_conv_dgrad_from_phase_weights():
+    from diffusion_e2e_ft_b200.backward_packing import pack_upsample_conv_dgrad
+    g = torch.Generator().manual_seed(7)
+    m = Upsample2D(8)
+    with torch.no_grad():
+        m.conv.weight.copy_((torch.randn(8, 8, 3, 3, generator=g) * 0.2).half().float())
+    x = torch.randn(1, 8, 5, 6, generator=g)
+    fwd = lambda t: F.conv2d(F.interpolate(t, scale_factor=2.0, mode="nearest"), m.conv.weight, padding=1)
+    dy = torch.randn(1, 8, 10, 12, generator=g).half().float()
+    want = _grad_input(fwd, x, dy).permute(0, 2, 3, 1)
+    got = torch.zeros_like(want)
+    dy_nhwc = dy.permute(0, 2, 3, 1)
+    for (py, px), (wp, taps) in pack_upsample_conv_dgrad(m._pack_phases()).items():
+        got += tap_conv_reference(dy_nhwc[:, py::2, px::2].contiguous(), wp, 8, taps)
+    assert torch.allclose(got, want, atol=3e-2), (got - want).abs().max()
