@@ -344,7 +344,70 @@ def _noswap(fn):
     return run
 
 
+# ------------------------------------------------------------------ backward (data-gradient) convs, row a10
+def _autograd_dx(fwd, x_nchw, dy_nchw):
+    x = x_nchw.clone().requires_grad_(True)
+    (fwd(x) * dy_nchw).sum().backward()
+    return x.grad.permute(0, 2, 3, 1)
+
+
+def check_conv_dgrad_s1(NB=2, H=20, W=24, Cin=128, Cout=192, seed=61):
+    from diffusion_e2e_ft_b200.backward_packing import pack_conv_dgrad_s1
+    w = _rand(Cout, Cin, 3, 3, seed=seed, scale=1.0 / math.sqrt(9 * Cin))
+    dy = _rand(NB, H, W, Cout, seed=seed + 1)
+    x = _rand(NB, Cin, H, W, seed=seed + 2, dtype=torch.float32)
+    wp, taps = pack_conv_dgrad_s1(w)
+    got = ops.conv2d(dy, wp, Cin, taps=taps, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    ref = _autograd_dx(lambda t: F.conv2d(t, w.float(), padding=1), x, dy.float().permute(0, 3, 1, 2))
+    return rel_l2(got, ref), 3e-5
+
+
+def check_conv_dgrad_s2(pad_lo=1, NB=2, H=20, W=24, Cin=128, Cout=128, seed=63):
+    from diffusion_e2e_ft_b200.backward_packing import pack_conv_dgrad_s2
+    w = _rand(Cout, Cin, 3, 3, seed=seed, scale=1.0 / math.sqrt(9 * Cin))
+    x = _rand(NB, Cin, H, W, seed=seed + 2, dtype=torch.float32)
+    if pad_lo:
+        fwd = lambda t: F.conv2d(t, w.float(), stride=2, padding=1)
+    else:
+        fwd = lambda t: F.conv2d(F.pad(t, (0, 1, 0, 1)), w.float(), stride=2)
+    dy = _rand(NB, H // 2, W // 2, Cout, seed=seed + 1)
+    got = torch.empty((NB, H, W, Cin), dtype=torch.float32, device=DEV)
+    for (py, px), (wp, taps) in pack_conv_dgrad_s2(w, pad_lo).items():
+        ops.conv2d(dy, wp, Cin, taps=taps, out_hw=(H // 2, W // 2), out=got, out_mul=2, out_off=(py, px))
+    torch.cuda.synchronize()
+    ref = _autograd_dx(fwd, x, dy.float().permute(0, 3, 1, 2))
+    return rel_l2(got, ref), 3e-5
+
+
+def check_upsample_conv_dgrad(NB=2, H=12, W=10, C=128, seed=65):
+    """dX of (nearest x2 -> conv3x3): four stride-2 tap convs over the full-resolution dY, accumulated through
+    the fp32 residual operand (phase (py,px) reads dY[2a + py - 2dy, 2b + px - 2dx])."""
+    from diffusion_e2e_ft_b200.backward_packing import pack_upsample_conv_dgrad
+    from diffusion_e2e_ft_b200.modules import Upsample2D
+    m = Upsample2D(C).to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        m.conv.weight.copy_((torch.randn(C, C, 3, 3, generator=g) / math.sqrt(9 * C)).half().float())
+    w = m.conv.weight.detach()
+    dy = _rand(NB, 2 * H, 2 * W, C, seed=seed + 1)
+    x = _rand(NB, C, H, W, seed=seed + 2, dtype=torch.float32)
+    acc = None
+    for (py, px), (wp, taps) in pack_upsample_conv_dgrad(m._pack_phases()).items():
+        taps2 = [(2 * ty + py, 2 * tx + px) for ty, tx in taps]
+        acc = ops.conv2d(dy, wp.to(DEV), C, taps=taps2, stride=2, out_hw=(H, W), residual=acc,
+                         out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    fwd = lambda t: F.conv2d(F.interpolate(t, scale_factor=2.0, mode="nearest"), w, padding=1)
+    ref = _autograd_dx(fwd, x, dy.float().permute(0, 3, 1, 2))
+    return rel_l2(acc, ref), 1e-3      # phase weights are sums of fp16 weights re-rounded to fp16
+
+
 CHECKS = {
+    "conv_dgrad_s1": check_conv_dgrad_s1,
+    "conv_dgrad_s2_pad1": lambda: check_conv_dgrad_s2(1),
+    "conv_dgrad_s2_vae_pad": lambda: check_conv_dgrad_s2(0),
+    "upsample_conv_dgrad": check_upsample_conv_dgrad,
     "linear_basic": lambda: check_linear(),
     "linear_small_m": lambda: check_linear(M=8, N=1280, K=320),
     "linear_bn256": lambda: check_linear(M=2000, N=1280, K=1280, seed=2),
