@@ -1,0 +1,129 @@
+"""Backward-pass operators of the fine-tuning step (reference training/train.py:545-566,
+`accelerator.backward(loss)`), composed from the tcgen05 GEMM / implicit-GEMM conv kernels with transposed or
+re-packed operands plus the streaming kernels in csrc/backward.cu.  Every function here is checked against
+torch.autograd on the B200 (tests/kernel_checks.py, `bwd_*`).
+
+Conventions: activations / incoming gradients that feed a GEMM are fp16 (the training step multiplies the loss
+by a static loss scale so they stay in range), parameter gradients are fp32, the gradient of the residual stream
+is fp32 unless stated.  Weight-gradient GEMMs contract over pixels (K = NB*H*W): both operands are brought into
+K-major form by `ops.gather_planar` (one pass each; a later version reads them MN-major straight from the
+NHWC tensors through the UMMA descriptor, like V in the attention kernel).
+"""
+import torch
+
+from . import ops
+from .backward_packing import pack_conv_dgrad_s1, pack_conv_dgrad_s2, pack_upsample_conv_dgrad
+from .ops import F16, F32, TAPS3
+
+
+# ------------------------------------------------------------------------------------------------ linear
+def linear_bwd(a, w, dy, need_da=True, da_dtype=F16, da_add=None, need_dw=True, bias=True):
+    """y = a @ w.T (+ b).  a [M,K] fp16, w [N,K] fp16, dy [M,N] fp16 (row-strided views allowed).
+    Returns (da [M,K] | None, dw fp32 [N,K] | None, db fp32 [N] | None)."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert dy.shape == (M, N) and N % 8 == 0 and K % 8 == 0
+    da = dw = db = None
+    if need_da:
+        wt = ops.transpose_rows(w)                                       # [K, N]
+        da = ops.linear(dy, wt, residual=da_add, out_dtype=da_dtype)
+    if need_dw:
+        dyt = ops.transpose_rows(dy)                                     # [N, ru8(M)]
+        at = ops.transpose_rows(a)                                       # [K, ru8(M)]
+        dw = ops.linear(dyt, at, out_dtype=F32)
+        if bias:
+            db = ops.col_sum(dy)
+    return da, dw, db
+
+
+# -------------------------------------------------------------------------------------------------- conv
+def conv_wgrad(x, dy, taps=TAPS3, stride=1, up=1, bias=True):
+    """Weight gradient of out[n,o,p,:] = sum_t Wp[:, t*Cin:(t+1)*Cin] @ x_up[n, stride*o+ty, stride*p+tx, :]
+    (x_up = nearest-`up`x of x).  x [NB,H,W,Cin], dy [NB,Ho,Wo,Cout] fp16 NHWC.
+    Returns (dWp fp32 [Cout, T*Cin] in the packed forward layout, db fp32 [Cout] | None)."""
+    NB, Ho, Wo, Cout = dy.shape
+    Cin = x.shape[3]
+    dyt = ops.gather_planar(dy)                                          # [Cout, P8]
+    dwp = torch.empty((Cout, len(taps) * Cin), dtype=F32, device=x.device)
+    for t, (ty, tx) in enumerate(taps):
+        xt = ops.gather_planar(x, out_hw=(Ho, Wo), stride=stride, up=up, off=(ty, tx))   # [Cin, P8]
+        ops.linear(dyt, xt, out=dwp[:, t * Cin:(t + 1) * Cin], out_dtype=F32)
+    db = ops.col_sum(dy.reshape(-1, Cout)) if bias else None
+    return dwp, db
+
+
+def unpack_conv_grad(dwp, cin, kh=3, kw=3):
+    """packed [Cout, kh*kw*Cin] -> parameter layout [Cout, Cin, kh, kw] (host-side re-layout of a gradient)."""
+    return dwp.view(dwp.shape[0], kh, kw, cin).permute(0, 3, 1, 2).contiguous()
+
+
+def conv_dgrad(dy, w, cin, kind="s1", out_dtype=F32, add=None, packed=None, in_hw=None):
+    """Data gradient of the path's convolutions on the forward conv kernel.
+    kind: "s1" (3x3 pad 1), "s2" (stride 2 pad 1), "s2_vae" (stride 2, pad (0,1,0,1)), "up" (nearest-2x + 3x3),
+    "1x1".  dy NHWC fp16; returns dx NHWC (`add`, same shape/dtype, is accumulated)."""
+    NB, Ho, Wo, Cout = dy.shape
+    if kind == "1x1":
+        wt = packed if packed is not None else ops.transpose_rows(w.reshape(w.shape[0], -1).to(F16))
+        return ops.conv2d(dy, wt, cin, taps=[(0, 0)], residual=add, out_dtype=out_dtype)
+    if kind == "s1":
+        wp, taps = packed if packed is not None else pack_conv_dgrad_s1(w)
+        return ops.conv2d(dy, wp, cin, taps=taps, residual=add, out_dtype=out_dtype)
+    if kind in ("s2", "s2_vae"):
+        ph = packed if packed is not None else pack_conv_dgrad_s2(w, 1 if kind == "s2" else 0)
+        H, W = in_hw if in_hw is not None else (2 * Ho, 2 * Wo)
+        assert (H, W) == (2 * Ho, 2 * Wo), "odd input sizes: pad dY on the host first"
+        out = torch.empty((NB, H, W, cin), dtype=out_dtype, device=dy.device)
+        for (py, px), (wp, taps) in ph.items():
+            ops.conv2d(dy, wp, cin, taps=taps, out_hw=(Ho, Wo), out=out, out_mul=2, out_off=(py, px), residual=add)
+        return out
+    if kind == "up":
+        acc = add
+        for (py, px), (wp, taps) in (packed if packed is not None else pack_upsample_conv_dgrad(w)).items():
+            taps2 = [(2 * ty + py, 2 * tx + px) for ty, tx in taps]
+            acc = ops.conv2d(dy, wp, cin, taps=taps2, stride=2, out_hw=(Ho // 2, Wo // 2), residual=acc,
+                             out_dtype=out_dtype)
+        return acc
+    raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------------------------- attention
+def attention_bwd(q, k, v, do, heads, scale):
+    """Backward of softmax(scale * q k^T) v per head (head dim 64), by recomputation: S and dP on the GEMM kernel,
+    row softmax + its backward, then dQ = dS K, dK = dS^T Q, dV = P^T dO.  q/do [B,T,heads*64], k/v [B,Tk,heads*64]
+    fp16 views (last dim contiguous).  Returns contiguous fp16 (dq, dk, dv).  Materialises [heads, T, Tk] per
+    image — the fused flash backward replaces this once the rest of a10 is in place."""
+    B, T, C = q.shape
+    Tk = k.shape[1]
+    assert C == heads * 64 and T % 8 == 0
+    Tkp = ops._ru8(Tk)
+    dev = q.device
+    dq = torch.empty((B, T, C), dtype=F16, device=dev)
+    dk = torch.empty((B, Tk, C), dtype=F16, device=dev)
+    dv = torch.empty((B, Tk, C), dtype=F16, device=dev)
+
+    def heads_view(t2d):                      # [L, heads*64] -> [heads, L, 64] strided view
+        return t2d.unflatten(-1, (heads, 64)).permute(1, 0, 2)
+
+    for b in range(B):
+        qh, kh, vh, doh = heads_view(q[b]), heads_view(k[b]), heads_view(v[b]), heads_view(do[b])
+        s = torch.zeros((heads, T, Tkp), dtype=F32, device=dev)
+        ops.linear(qh, kh, out=s[:, :, :Tk], out_dtype=F32)
+        p = ops.softmax_rows(s, scale, cols=Tk)                          # [heads, T, Tkp] fp16, padding 0
+        dp = torch.zeros((heads, T, Tkp), dtype=F32, device=dev)
+        ops.linear(doh, vh, out=dp[:, :, :Tk], out_dtype=F32)
+        ds = ops.softmax_bwd_rows(p, dp, scale, cols=Tk)                 # [heads, T, Tkp] fp16, padding 0
+        del s, dp
+        # dQ[h] = dS[h] @ K[h]: contraction over keys -> K^T [64, Tkp] per head
+        kt = ops.transpose_rows(k[b]).view(heads, 64, Tkp)
+        ops.linear(ds, kt, out=heads_view(dq[b]))
+        # dK[h] = dS[h]^T @ Q[h], dV[h] = P[h]^T @ dO[h]: contraction over queries
+        qt = ops.transpose_rows(q[b]).view(heads, 64, T)
+        dot = ops.transpose_rows(do[b]).view(heads, 64, T)
+        dst = ops.gather_planar(ds.view(heads, 1, T, Tkp))               # [Tkp, heads*T]
+        pt = ops.gather_planar(p.view(heads, 1, T, Tkp))
+        ld = dst.stride(0)
+        dst_h = dst.as_strided((heads, Tk, T), (T, ld, 1))
+        pt_h = pt.as_strided((heads, Tk, T), (T, ld, 1))
+        ops.linear(dst_h, qt, out=heads_view(dk[b]))
+        ops.linear(pt_h, dot, out=heads_view(dv[b]))
+    return dq, dk, dv

@@ -46,6 +46,18 @@ _SIGS = {
     "b200_sumsq": (c_int, [_P, _LL, _P, _P]),
     "b200_adamw_step": (c_int, [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_float, c_int, _P,
                                 c_float, _P]),
+    "b200_gather_planar": (c_int, [_P, c_int, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P,
+                                   _LL, _P]),
+    "b200_col_sum": (c_int, [_P, c_int, _LL, c_int, _LL, _P, _P]),
+    "b200_group_norm_mean_rstd": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, _P, _P]),
+    "b200_group_norm_bwd_sums": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, c_int,
+                                         _P, _P]),
+    "b200_group_norm_bwd_apply": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, c_int,
+                                          _P, _P, _P, c_int, _P]),
+    "b200_layer_norm_bwd": (c_int, [_P, c_int, _LL, c_int, _P, _P, c_float, _P, _P, c_int, _P, _P, _P]),
+    "b200_softmax_bwd_rows": (c_int, [_P, _LL, _P, _LL, _P, _LL, c_int, c_float, _P]),
+    "b200_act_bwd": (c_int, [_P, _P, _LL, c_int, _P, _P]),
+    "b200_geglu_bwd": (c_int, [_P, _P, _LL, _P, _LL, c_int, _P, _P, _LL, _P]),
     "b200_cast_f32_to_f16": (c_int, [_P, _P, _LL, _P]),
     "b200_nhwc_to_nchw_f32": (c_int, [_P, c_int, c_int, c_int, _LL, _P, _P]),
 }

@@ -340,7 +340,7 @@ def softmax_rows(s, scale, cols=None):
     ld = s.shape[-1]
     cols = cols or ld
     rows = s.numel() // ld
-    p = torch.empty(s.shape, dtype=F16, device=s.device)
+    p = (torch.zeros if cols != ld else torch.empty)(s.shape, dtype=F16, device=s.device)   # padding stays 0
     _ck(_lib.load().b200_softmax_rows(_p(s), ld, _p(p), ld, rows, cols, float(scale), _stream()),
                "b200_softmax_rows")
     return p
@@ -467,3 +467,150 @@ def nhwc_to_nchw_f32(x):
     _ck(_lib.load().b200_nhwc_to_nchw_f32(_p(x), int(x.dtype == F32), NB, C, H * W, _p(y), _stream()),
                "b200_nhwc_to_nchw_f32")
     return y
+
+
+# ------------------------------------------------------------------------------ backward-pass kernels (row a10)
+def _ru8(n):
+    return (n + 7) // 8 * 8
+
+
+@_timed("bwd_gather")
+def gather_planar(x, out_hw=None, stride=1, up=1, off=(0, 0)):
+    """x: [NB,H,W,C] fp16/fp32 whose last dim is contiguous and whose pixels are uniformly strided (a channel
+    slice of an NHWC tensor is fine) -> fp16 [C, ru8(NB*Ho*Wo)] with
+    out[c][(n*Ho+o)*Wo+p] = x[n, (stride*o+off_y)//up, (stride*p+off_x)//up, c] (zero outside / in the padding)."""
+    _need_cuda(x)
+    NB, H, W, C = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and (NB == 1 or x.stride(0) == H * x.stride(1)), x.stride()
+    Ho, Wo = out_hw if out_hw is not None else (H, W)
+    P = NB * Ho * Wo
+    out = torch.empty((C, _ru8(P)), dtype=F16, device=x.device)
+    _ck(_lib.load().b200_gather_planar(_p(x), int(x.dtype == F32), x.stride(2), NB, H, W, C, Ho, Wo, stride, up,
+                                       off[0], off[1], _p(out), out.stride(0), _stream()), "b200_gather_planar")
+    return out
+
+
+def transpose_rows(a):
+    """[R, C] (row-strided view allowed) -> fp16 [C, ru8(R)], zero padded."""
+    assert a.dim() == 2
+    R, ld = a.shape[0], a.stride(0)
+    return gather_planar(a.as_strided((1, 1, R, a.shape[1]), (R * ld, R * ld, ld, 1), a.storage_offset()))
+
+
+@_timed("bwd_misc")
+def col_sum(x, out=None):
+    """sum over rows of a [rows, C] (row-strided) fp16/fp32 matrix -> fp32 [C] (accumulated into `out`)."""
+    _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.zeros((x.shape[1],), dtype=F32, device=x.device)
+    _ck(_lib.load().b200_col_sum(_p(x), int(x.dtype == F32), x.shape[0], x.shape[1], x.stride(0), _p(out), _stream()),
+        "b200_col_sum")
+    return out
+
+
+def group_norm_mean_rstd(x1, eps, groups=32, x2=None):
+    """(mean, rstd) [NB, groups, 2] fp32 of the channel-concat [x1 | x2], from the per-channel sums attached by
+    the producing kernels when present, else by a statistics pass."""
+    _need_cuda(x1, x2)
+    NB, H, W, C1 = x1.shape
+    C2 = x2.shape[3] if x2 is not None else 0
+    L = _lib.load()
+    mr = torch.empty((NB, groups, 2), dtype=F32, device=x1.device)
+    cs1 = getattr(x1, "_cs", None)
+    cs2 = getattr(x2, "_cs", None) if x2 is not None else None
+    if FUSE_GN_STATS and cs1 is not None and (x2 is None or cs2 is not None):
+        _ck(L.b200_group_norm_mean_rstd(None, _p(cs1), C1, _p(cs2), C2, NB, H * W, groups, float(eps), _p(mr), _stream()),
+            "b200_group_norm_mean_rstd")
+        return mr
+    sums = torch.zeros((NB, groups, 2), dtype=torch.float64, device=x1.device)
+    _ck(L.b200_group_norm_stats(_p(x1), C1, _p(x2), C2, int(x1.dtype == F32), NB, H * W, groups, _p(sums), _stream()),
+        "b200_group_norm_stats")
+    _ck(L.b200_group_norm_mean_rstd(_p(sums), None, C1, None, C2, NB, H * W, groups, float(eps), _p(mr), _stream()),
+        "b200_group_norm_mean_rstd")
+    return mr
+
+
+@_timed("bwd_group_norm")
+def group_norm_bwd(xs, dy, mr, gamma, beta, groups=32, silu=True, adds=None, out_dtype=F32):
+    """Backward of group_norm over the channel-concat of `xs` (list of 1 or 2 NHWC tensors).  dy: fp16
+    [NB,H,W,sum C].  Returns ([dx per input], dgamma, dbeta); `adds[i]` (same shape/dtype as dx_i) is added."""
+    _need_cuda(dy, *xs)
+    assert dy.dtype == F16 and dy.is_contiguous()
+    NB, H, W, Ctot = dy.shape
+    assert sum(x.shape[3] for x in xs) == Ctot
+    L = _lib.load()
+    S = torch.zeros((NB, Ctot, 2), dtype=F32, device=dy.device)
+    off = 0
+    for x in xs:
+        assert x.is_contiguous() and x.shape[:3] == dy.shape[:3]
+        _ck(L.b200_group_norm_bwd_sums(_p(x), int(x.dtype == F32), x.shape[3], off, Ctot, _p(dy), NB, H * W, groups,
+                                       _p(mr), _p(gamma), _p(beta), int(silu), _p(S), _stream()),
+            "b200_group_norm_bwd_sums")
+        off += x.shape[3]
+    dxs, off = [], 0
+    for i, x in enumerate(xs):
+        add = adds[i] if adds is not None else None
+        dx = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        if add is not None:
+            assert add.dtype == out_dtype and add.is_contiguous() and add.shape == x.shape
+        _ck(L.b200_group_norm_bwd_apply(_p(x), int(x.dtype == F32), x.shape[3], off, Ctot, _p(dy), NB, H * W, groups,
+                                        _p(mr), _p(gamma), _p(beta), int(silu), _p(S), _p(add), _p(dx),
+                                        int(out_dtype == F32), _stream()), "b200_group_norm_bwd_apply")
+        dxs.append(dx)
+        off += x.shape[3]
+    dparam = S.sum(0)                       # [Ctot, 2]: (d_beta, d_gamma) — a [NB, C, 2] reduction, host plumbing
+    return dxs, dparam[:, 1].contiguous(), dparam[:, 0].contiguous()
+
+
+@_timed("bwd_layer_norm")
+def layer_norm_bwd(x, dy, gamma, eps=1e-5, add=None, out_dtype=F32, dgamma=None, dbeta=None):
+    _need_cuda(x, dy)
+    assert x.is_contiguous() and dy.is_contiguous() and dy.dtype == F16 and dy.shape == x.shape
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    if add is not None:
+        assert add.dtype == out_dtype and add.is_contiguous() and add.shape == x.shape
+    dgamma = torch.zeros((C,), dtype=F32, device=x.device) if dgamma is None else dgamma
+    dbeta = torch.zeros((C,), dtype=F32, device=x.device) if dbeta is None else dbeta
+    _ck(_lib.load().b200_layer_norm_bwd(_p(x), int(x.dtype == F32), rows, C, _p(gamma), _p(dy), float(eps), _p(add),
+                                        _p(dx), int(out_dtype == F32), _p(dgamma), _p(dbeta), _stream()),
+        "b200_layer_norm_bwd")
+    return dx, dgamma, dbeta
+
+
+@_timed("bwd_softmax")
+def softmax_bwd_rows(p, dp, scale, cols=None):
+    """p: fp16 [..., ld] probabilities, dp: fp32 same layout -> dS fp16 (padding columns zero)."""
+    _need_cuda(p, dp)
+    assert p.dtype == F16 and dp.dtype == F32 and p.is_contiguous() and dp.is_contiguous() and p.shape == dp.shape
+    ld = p.shape[-1]
+    cols = cols or ld
+    ds = (torch.zeros if cols != ld else torch.empty)(p.shape, dtype=F16, device=p.device)
+    _ck(_lib.load().b200_softmax_bwd_rows(_p(p), ld, _p(dp), ld, _p(ds), p.numel() // ld, cols, float(scale), _stream()),
+        "b200_softmax_bwd_rows")
+    return ds
+
+
+@_timed("bwd_misc")
+def act_bwd(x, dy, act):
+    _need_cuda(x, dy)
+    assert x.dtype == F16 and dy.dtype == F16 and x.is_contiguous() and dy.is_contiguous() and x.shape == dy.shape
+    dx = torch.empty_like(x)
+    _ck(_lib.load().b200_act_bwd(_p(x), _p(dy), x.numel(), act, _p(dx), _stream()), "b200_act_bwd")
+    return dx
+
+
+@_timed("bwd_misc")
+def geglu_bwd(hg, dy):
+    """hg: fp16 [rows, 2*inner] = [value | gate] pre-activations of the GEGLU projection; dy: [rows, inner].
+    Returns d(hg) [rows, 2*inner] fp16."""
+    _need_cuda(hg, dy)
+    assert hg.dtype == F16 and dy.dtype == F16 and hg.is_contiguous() and dy.is_contiguous()
+    rows, inner = dy.shape
+    assert hg.shape == (rows, 2 * inner)
+    d = torch.empty_like(hg)
+    _ck(_lib.load().b200_geglu_bwd(_p(hg), _p(hg[:, inner:]), 2 * inner, _p(dy), rows, inner, _p(d), _p(d[:, inner:]),
+                                   2 * inner, _stream()), "b200_geglu_bwd")
+    return d

@@ -173,6 +173,42 @@ int b200_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     const double* grad_norm_sq, float max_grad_norm, void* stream);
 
+/* ---- Backward pass (training/train.py:545-566, `accelerator.backward(loss)`).  The GEMM-shaped halves run on
+ * b200_linear / b200_conv2d_nhwc with re-packed operands; these are the streaming / reduction kernels around them.
+ *
+ * b200_gather_planar: out[c][q] (fp16, row stride ldo >= NB*Ho*Wo, zero-filled past the last pixel) =
+ *   x[n][(stride*o + oy)/up][(stride*p + ox)/up][c] (pixel stride ldx >= C) with q = (n*Ho + o)*Wo + p, zero outside the (up-sampled)
+ *   image: the K-major (K = pixels) operand of a weight-gradient GEMM for one kernel tap of a stride-1/-2 or
+ *   nearest-2x-upsampled 3x3 conv; with Ho=H, Wo=W, stride=1, up=1, oy=ox=0 a plain [rows][C] -> [C][rows] transpose.
+ * b200_col_sum: out[c] += sum_rows x[row][c] (bias gradients).
+ * GroupNorm backward (diffusers GroupNorm(32) + optional SiLU, NHWC): mean_rstd [NB][groups][2] from the
+ *   forward's statistics; pass 1 accumulates S [NB][Ctot][2] = (sum dz, sum dz*xhat) per channel (zeroed by
+ *   the caller; call once per concatenated input with its channel offset), pass 2 writes
+ *   dx = rstd*(dz*gamma - mean_g(gamma dz) - xhat*mean_g(gamma dz xhat)) (+ add).  d_gamma = sum_n S[..1],
+ *   d_beta = sum_n S[..0].  dy is fp16 [NB][HW][Ctot].
+ * b200_layer_norm_bwd: dx (+ add) and d_gamma/d_beta (accumulated into zeroed fp32 [C]).
+ * b200_softmax_bwd_rows: dS = scale * P o (dP - rowsum(dP o P)), P/dS fp16, dP fp32.
+ * b200_act_bwd: dx = dy * act'(x), act = B200_ACT_SILU | B200_ACT_GELU (fp16).
+ * b200_geglu_bwd: y = h*gelu(g): dh = dy*gelu(g), dg = dy*h*gelu'(g). */
+int b200_gather_planar(const void* x, int in_f32, long long ldx, int NB, int H, int W, int C, int Ho, int Wo, int stride, int up,
+                       int oy, int ox, void* out, long long ldo, void* stream);
+int b200_col_sum(const void* x, int in_f32, long long rows, int C, long long ld, float* out, void* stream);
+int b200_group_norm_mean_rstd(const double* sums, const float* cs1, int C1, const float* cs2, int C2, int NB, int HW,
+                              int groups, float eps, float* mean_rstd, void* stream);
+int b200_group_norm_bwd_sums(const void* x, int in_f32, int Cx, int c_off, int Ctot, const void* dy, int NB, int HW,
+                             int groups, const float* mean_rstd, const float* gamma, const float* beta, int silu,
+                             float* S, void* stream);
+int b200_group_norm_bwd_apply(const void* x, int in_f32, int Cx, int c_off, int Ctot, const void* dy, int NB, int HW,
+                              int groups, const float* mean_rstd, const float* gamma, const float* beta, int silu,
+                              const float* S, const void* add, void* dx, int out_f32, void* stream);
+int b200_layer_norm_bwd(const void* x, int in_f32, long long rows, int C, const float* gamma, const void* dy,
+                        float eps, const void* add, void* dx, int out_f32, float* dgamma, float* dbeta, void* stream);
+int b200_softmax_bwd_rows(const void* P, long long ldp, const float* dP, long long ldd, void* dS, long long rows,
+                          int cols, float scale, void* stream);
+int b200_act_bwd(const void* x, const void* dy, long long n, int act, void* dx, void* stream);
+int b200_geglu_bwd(const void* h, const void* g, long long ld_hg, const void* dy, long long rows, int inner, void* dh,
+                   void* dg, long long ld_d, void* stream);
+
 /* fp32 <-> fp16 casts / layout helpers used at module boundaries. */
 int b200_cast_f32_to_f16(const float* x, void* y, long long n, void* stream);
 int b200_nhwc_to_nchw_f32(const void* x, int in_f32, int NB, int C, long long HW, float* y, void* stream);

@@ -471,3 +471,9 @@ CHECKS = {
     "losses_ssi_angular": check_losses,
     "adamw_clip_fused": check_adamw,
 }
+
+
+# backward-pass operators (row a10): tests/bwd_checks.py
+from bwd_checks import BWD_CHECKS  # noqa: E402
+
+CHECKS.update(BWD_CHECKS)
