@@ -71,11 +71,18 @@ def conv_dgrad(dy, w, cin, kind="s1", out_dtype=F32, add=None, packed=None, in_h
     if kind in ("s2", "s2_vae"):
         ph = packed if packed is not None else pack_conv_dgrad_s2(w, 1 if kind == "s2" else 0)
         H, W = in_hw if in_hw is not None else (2 * Ho, 2 * Wo)
-        assert (H, W) == (2 * Ho, 2 * Wo), "odd input sizes: pad dY on the host first"
-        out = torch.empty((NB, H, W, cin), dtype=out_dtype, device=dy.device)
+        even = (H, W) == (2 * Ho, 2 * Wo)
+        assert even or (kind == "s2" and 2 * Ho - H in (0, 1) and 2 * Wo - W in (0, 1)), (H, W, Ho, Wo)
+        out = torch.empty((NB, 2 * Ho, 2 * Wo, cin), dtype=out_dtype, device=dy.device)
         for (py, px), (wp, taps) in ph.items():
-            ops.conv2d(dy, wp, cin, taps=taps, out_hw=(Ho, Wo), out=out, out_mul=2, out_off=(py, px), residual=add)
-        return out
+            ops.conv2d(dy, wp, cin, taps=taps, out_hw=(Ho, Wo), out=out, out_mul=2, out_off=(py, px),
+                       residual=add if even else None)
+        if even:
+            return out
+        # odd input size (pad-1 stride-2 conv): the extra row/column of the even-sized buffer is the forward's
+        # zero padding; crop it (host-side re-layout, only on sizes that are not multiples of 2)
+        out = out[:, :H, :W].contiguous()
+        return out if add is None else out.add_(add)
     if kind == "up":
         acc = add
         for (py, px), (wp, taps) in (packed if packed is not None else pack_upsample_conv_dgrad(w)).items():
@@ -87,22 +94,36 @@ def conv_dgrad(dy, w, cin, kind="s1", out_dtype=F32, add=None, packed=None, in_h
 
 
 # --------------------------------------------------------------------------------------------- attention
-def attention_bwd(q, k, v, do, heads, scale):
+def attention_bwd(q, k, v, do, heads, scale, outs=None):
     """Backward of softmax(scale * q k^T) v per head (head dim 64), by recomputation: S and dP on the GEMM kernel,
     row softmax + its backward, then dQ = dS K, dK = dS^T Q, dV = P^T dO.  q/do [B,T,heads*64], k/v [B,Tk,heads*64]
-    fp16 views (last dim contiguous).  Returns contiguous fp16 (dq, dk, dv).  Materialises [heads, T, Tk] per
-    image — the fused flash backward replaces this once the rest of a10 is in place."""
+    fp16 views (last dim contiguous).  Returns fp16 (dq, dk, dv) — written into `outs` (row-strided views, e.g. the
+    three column blocks of a fused d(qkv) buffer) when given.  Materialises [heads, T, Tk] per image — the fused
+    flash backward replaces this once the rest of a10 is in place."""
     B, T, C = q.shape
     Tk = k.shape[1]
-    assert C == heads * 64 and T % 8 == 0
-    Tkp = ops._ru8(Tk)
+    assert C == heads * 64
+    Tkp, T8 = ops._ru8(Tk), ops._ru8(T)
     dev = q.device
-    dq = torch.empty((B, T, C), dtype=F16, device=dev)
-    dk = torch.empty((B, Tk, C), dtype=F16, device=dev)
-    dv = torch.empty((B, Tk, C), dtype=F16, device=dev)
+    if outs is not None:
+        dq, dk, dv = outs
+        assert dq.shape == (B, T, C) and dk.shape == (B, Tk, C) and dv.shape == (B, Tk, C)
+    else:
+        dq = torch.empty((B, T, C), dtype=F16, device=dev)
+        dk = torch.empty((B, Tk, C), dtype=F16, device=dev)
+        dv = torch.empty((B, Tk, C), dtype=F16, device=dev)
 
     def heads_view(t2d):                      # [L, heads*64] -> [heads, L, 64] strided view
         return t2d.unflatten(-1, (heads, 64)).permute(1, 0, 2)
+
+    def transpose_per_head(m):                # [heads, T, Tkp] -> [heads, Tkp, T8] (zero padded queries)
+        if T == T8:                           # one launch: [Tkp, heads*T], head h = columns h*T .. (h+1)*T
+            t = ops.gather_planar(m.view(heads, 1, T, Tkp))
+            return t.as_strided((heads, Tkp, T), (T, t.stride(0), 1))
+        t = torch.empty((heads, Tkp, T8), dtype=F16, device=dev)
+        for h in range(heads):
+            ops.gather_planar(m[h].view(1, 1, T, Tkp), out=t[h])
+        return t
 
     for b in range(B):
         qh, kh, vh, doh = heads_view(q[b]), heads_view(k[b]), heads_view(v[b]), heads_view(do[b])
@@ -116,14 +137,9 @@ def attention_bwd(q, k, v, do, heads, scale):
         # dQ[h] = dS[h] @ K[h]: contraction over keys -> K^T [64, Tkp] per head
         kt = ops.transpose_rows(k[b]).view(heads, 64, Tkp)
         ops.linear(ds, kt, out=heads_view(dq[b]))
-        # dK[h] = dS[h]^T @ Q[h], dV[h] = P[h]^T @ dO[h]: contraction over queries
-        qt = ops.transpose_rows(q[b]).view(heads, 64, T)
-        dot = ops.transpose_rows(do[b]).view(heads, 64, T)
-        dst = ops.gather_planar(ds.view(heads, 1, T, Tkp))               # [Tkp, heads*T]
-        pt = ops.gather_planar(p.view(heads, 1, T, Tkp))
-        ld = dst.stride(0)
-        dst_h = dst.as_strided((heads, Tk, T), (T, ld, 1))
-        pt_h = pt.as_strided((heads, Tk, T), (T, ld, 1))
-        ops.linear(dst_h, qt, out=heads_view(dk[b]))
-        ops.linear(pt_h, dot, out=heads_view(dv[b]))
+        # dK[h] = dS[h]^T @ Q[h], dV[h] = P[h]^T @ dO[h]: contraction over queries (zero padded to T8)
+        qt = ops.transpose_rows(q[b]).view(heads, 64, T8)
+        dot = ops.transpose_rows(do[b]).view(heads, 64, T8)
+        ops.linear(transpose_per_head(ds)[:, :Tk], qt, out=heads_view(dk[b]))
+        ops.linear(transpose_per_head(p)[:, :Tk], dot, out=heads_view(dv[b]))
     return dq, dk, dv

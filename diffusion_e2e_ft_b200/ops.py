@@ -475,7 +475,7 @@ def _ru8(n):
 
 
 @_timed("bwd_gather")
-def gather_planar(x, out_hw=None, stride=1, up=1, off=(0, 0)):
+def gather_planar(x, out_hw=None, stride=1, up=1, off=(0, 0), out=None):
     """x: [NB,H,W,C] fp16/fp32 whose last dim is contiguous and whose pixels are uniformly strided (a channel
     slice of an NHWC tensor is fine) -> fp16 [C, ru8(NB*Ho*Wo)] with
     out[c][(n*Ho+o)*Wo+p] = x[n, (stride*o+off_y)//up, (stride*p+off_x)//up, c] (zero outside / in the padding)."""
@@ -484,7 +484,9 @@ def gather_planar(x, out_hw=None, stride=1, up=1, off=(0, 0)):
     assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and (NB == 1 or x.stride(0) == H * x.stride(1)), x.stride()
     Ho, Wo = out_hw if out_hw is not None else (H, W)
     P = NB * Ho * Wo
-    out = torch.empty((C, _ru8(P)), dtype=F16, device=x.device)
+    if out is None:
+        out = torch.empty((C, _ru8(P)), dtype=F16, device=x.device)
+    assert out.dtype == F16 and out.shape[0] == C and out.shape[1] >= P and out.is_contiguous() and out.shape[1] % 8 == 0
     _ck(_lib.load().b200_gather_planar(_p(x), int(x.dtype == F32), x.stride(2), NB, H, W, C, Ho, Wo, stride, up,
                                        off[0], off[1], _p(out), out.stride(0), _stream()), "b200_gather_planar")
     return out

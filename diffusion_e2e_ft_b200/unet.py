@@ -178,10 +178,9 @@ class B200UNet2DConditionModel(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, return_dict=True, **unused):
-        if not sample.is_cuda:
-            raise RuntimeError("B200UNet2DConditionModel runs on sm_100a only (no CPU fallback)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward through the engine is not implemented yet; wrap in torch.no_grad()")
+        ops._need_cuda(sample)                                                      # sm_100a only, no CPU fallback
+        if torch.is_grad_enabled() and (sample.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_train(sample, timestep, encoder_hidden_states, class_labels, return_dict)
         cfg, sdt = self.config, self.stream_dtype
         B, _, H, W = sample.shape
         dev = sample.device
@@ -247,6 +246,68 @@ class B200UNet2DConditionModel(nn.Module):
         if not hasattr(self, "_conv_out_run") or self._conv_out_run.conv is not self.conv_out:
             self._conv_out_run = ConvOutSmall(self.conv_norm_out, self.conv_out)
         out = self._conv_out_run.run(x)
+        if out.dtype != sample.dtype:
+            out = out.to(sample.dtype)
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(out)
+
+
+    # ------------------------------------------------------------------ differentiable forward (row a10)
+    def _forward_train(self, sample, timestep, encoder_hidden_states, class_labels, return_dict):
+        """Same graph as `forward`, every block executed as a torch.autograd.Function (autograd_blocks.py) so
+        `loss.backward()` fills `.grad` of the parameters exactly like the reference's training/train.py:563."""
+        from . import autograd_blocks as ab
+        if self.stream_dtype != F32:
+            raise NotImplementedError("training runs with the fp32 residual stream (stream_dtype=torch.float32)")
+        cfg = self.config
+        B, _, H, W = sample.shape
+        dev = sample.device
+        n_up = len(cfg["block_out_channels"]) - 1
+        if (H % (2 ** n_up) != 0) or (W % (2 ** n_up) != 0):
+            raise NotImplementedError("training needs latent sizes divisible by %d for now" % (2 ** n_up))
+        if not torch.is_tensor(timestep):
+            t = torch.full((B,), float(timestep), dtype=F32, device=dev)
+        else:
+            t = timestep.to(device=dev, dtype=F32).reshape(-1).expand(B).contiguous()
+        if self.class_embedding is not None and class_labels is None:
+            raise ValueError("class_labels should be provided when num_class_embeds > 0")
+        temb_all = ab.embed(self, t, class_labels)
+        ep = self._embed_packed()
+        resnets = list(self._resnets())
+        temb_of = {id(r): temb_all[:, o:o + r.cout] for r, o in zip(resnets, ep["offs"])}
+        ctx16 = encoder_hidden_states.detach().to(F16).contiguous()
+
+        if not hasattr(self, "_conv_in_run") or self._conv_in_run.conv is not self.conv_in:
+            self._conv_in_run = ConvInSmall(self.conv_in)
+        x = ab.conv_in(self._conv_in_run, (sample if sample.dtype in (F16, F32) else sample.float()).detach())
+        skips = [x]
+        for blk in self.down_blocks:
+            for i, r in enumerate(blk.resnets):
+                last = (i == len(blk.resnets) - 1) and blk.downsamplers is not None
+                x = ab.resnet(r, x, temb_of[id(r)], None, f16_copy=last and blk.attentions is None)
+                if blk.attentions is not None:
+                    x = ab.transformer(blk.attentions[i], x, ctx16, f16_copy=last)
+                skips.append(x)
+            if blk.downsamplers is not None:
+                x = ab.downsample(blk.downsamplers[0], x)
+                skips.append(x)
+        mb = self.mid_block
+        x = ab.resnet(mb.resnets[0], x, temb_of[id(mb.resnets[0])])
+        x = ab.transformer(mb.attentions[0], x, ctx16)
+        x = ab.resnet(mb.resnets[1], x, temb_of[id(mb.resnets[1])])
+        for blk in self.up_blocks:
+            for i, r in enumerate(blk.resnets):
+                skip = skips.pop()
+                last = (i == len(blk.resnets) - 1) and blk.upsamplers is not None
+                x = ab.resnet(r, x, temb_of[id(r)], skip, f16_copy=last and blk.attentions is None)
+                if blk.attentions is not None:
+                    x = ab.transformer(blk.attentions[i], x, ctx16, f16_copy=last)
+            if blk.upsamplers is not None:
+                x = ab.upsample(blk.upsamplers[0], x)
+        if not hasattr(self, "_conv_out_run") or self._conv_out_run.conv is not self.conv_out:
+            self._conv_out_run = ConvOutSmall(self.conv_norm_out, self.conv_out)
+        out = ab.conv_out(self._conv_out_run, x)
         if out.dtype != sample.dtype:
             out = out.to(sample.dtype)
         if not return_dict:

@@ -244,6 +244,8 @@ BWD_CHECKS = {
     "bwd_gelu": lambda: check_act_bwd(ops.ACT_GELU),
     "bwd_geglu": lambda: check_geglu_bwd(),
     "bwd_attention_self": lambda: check_attention_bwd(),
+    "bwd_attention_self_t300": lambda: check_attention_bwd(B=1, T=300, Tk=300, heads=2, seed=29),
+    "bwd_attention_cross77_t4": lambda: check_attention_bwd(B=2, T=4, Tk=77, heads=4, fused_qkv=False, seed=33),
     "bwd_attention_cross77": lambda: check_attention_bwd(T=256, Tk=77, heads=5, fused_qkv=False),
 }
 

@@ -177,3 +177,35 @@ def run_training_forward_tiny(device="cuda:0", modality="depth"):
     got, _ = e2e_ft_forward(unet, vae, DDIMScheduler(), rgb.to(device), gt.to(device), mask.to(device), ctx.to(device),
                             modality)
     return dict(loss_engine=got.item(), loss_oracle=want.item(), rel_err=abs(got.item() - want.item()) / abs(want.item()))
+
+
+def run_unet_backward_tiny(device="cuda:0", hw=(16, 16), ctx_tokens=77):
+    """Row a10: gradients of every UNet parameter through the engine's autograd blocks vs torch.autograd through
+    the fp32 oracle, same weights / inputs / upstream gradient (bs=2).  Returns the forward error, the global
+    relative L2 error over all parameter gradients and the worst single parameter."""
+    unet_ref, _ = MG.build_tiny()
+    unet, _ = engine_from_oracle(unet_ref, None, device)
+    unet.requires_grad_(True)
+    unet_ref.requires_grad_(True)
+    x = MG.inputs(1, 2, 8, *hw)
+    c = MG.inputs(2, 2, ctx_tokens, 128, scale=0.5)
+    dy = MG.inputs(7, 2, 4, *hw)
+    y = unet(x.to(device), 999, c.to(device)).sample
+    (y * dy.to(device)).sum().backward()
+    yr = unet_ref(x, 999, c).sample
+    (yr * dy).sum().backward()
+    ref = dict(unet_ref.named_parameters())
+    num = den = 0.0
+    worst, worst_name, missing = 0.0, None, []
+    for n, p in unet.named_parameters():
+        if p.grad is None:
+            missing.append(n)
+            continue
+        gr = ref[n].grad
+        e = rel_l2(p.grad, gr)
+        if e > worst:
+            worst, worst_name = e, n
+        num += (p.grad.detach().float().cpu() - gr).pow(2).sum().item()
+        den += gr.pow(2).sum().item()
+    return dict(forward=rel_l2(y, yr), grad_global=(num / den) ** 0.5, grad_worst=worst, worst_name=worst_name,
+                missing=missing, n_params=len(ref))

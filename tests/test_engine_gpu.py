@@ -81,3 +81,13 @@ def test_training_step_forward_loss_matches_oracle(modality):
     r = EC.run_training_forward_tiny(modality=modality)
     print(r)
     assert r["rel_err"] <= 3e-3, r
+
+
+@pytest.mark.gpu
+def test_unet_backward_matches_oracle_autograd():
+    """`loss.backward()` through the engine UNet (autograd blocks on the CUDA backward operators)
+    vs torch.autograd through the fp32 oracle.  fp16 GEMM operands in both directions: 2e-2 per parameter."""
+    r = EC.run_unet_backward_tiny()
+    assert not r["missing"], r["missing"]
+    assert r["forward"] <= 3e-3, r
+    assert r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2, r
