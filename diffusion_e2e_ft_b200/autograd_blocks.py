@@ -491,3 +491,131 @@ class _EmbedFn(torch.autograd.Function):
 
 def embed(unet, t, class_labels):
     return _EmbedFn.apply(unet, t, class_labels, *_embed_params(unet))
+
+
+# ------------------------------------------------------------------------------------ VAE mid-block attention
+class _VAEAttentionFn(torch.autograd.Function):
+    """VAEAttention.run (single head, d = channels) + its data gradient.  The VAE is frozen in the fine-tuning
+    recipe (training/train.py:323-326), so only d/dx is produced."""
+
+    @staticmethod
+    def forward(ctx, m, box, x):
+        pk = m._pk.get(list(m.parameters()), lambda: dict(
+            g=_f32(m.group_norm.weight), b=_f32(m.group_norm.bias),
+            wqk=_f16(torch.cat([m.to_q.weight, m.to_k.weight], 0)),
+            bqk=_f32(torch.cat([m.to_q.bias, m.to_k.bias], 0)),
+            wv=_f16(m.to_v.weight), bv=_f32(m.to_v.bias),
+            wo=_f16(m.to_out[0].weight), bo=_f32(m.to_out[0].bias)))
+        B, H, W, C = x.shape
+        L = H * W
+        Lp = ops._ru8(L)
+        mr = ops.group_norm_mean_rstd(x, m.eps, m.groups)
+        hn = ops.group_norm(x, pk["g"], pk["b"], m.eps, m.groups, False).view(B, L, C)
+        qk = ops.linear(hn.view(B * L, C), pk["wqk"], pk["bqk"]).view(B, L, 2 * C)
+        vt_buf = torch.empty((B, C, Lp), dtype=F16, device=x.device)
+        vt = ops.linear(pk["wv"], hn, pk["bv"], bias_row=True, out=vt_buf[:, :, :L])
+        s_buf = torch.empty((B, L, Lp), dtype=F32, device=x.device)
+        ops.linear(qk[..., :C], qk[..., C:], out=s_buf[:, :, :L])
+        p_buf = ops.softmax_rows(s_buf, C ** -0.5, cols=L)
+        o = ops.linear(p_buf[:, :, :L], vt)
+        out = ops.linear(o.view(B * L, C), pk["wo"], pk["bo"], residual=x.view(B * L, C), out_dtype=F32,
+                         stats_rows_per_img=L)
+        ctx.m, ctx.saved = m, (x, mr, hn, qk, p_buf, o)
+        cs = getattr(out, "_cs", None)
+        if cs is not None:
+            box["_cs"] = cs
+        return out.view(B, H, W, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        m = ctx.m
+        x, mr, hn, qk, p_buf, o = ctx.saved
+        pk = m._pk._val
+        if any(p.requires_grad for p in m.parameters()):
+            raise NotImplementedError("the VAE attention block is differentiable w.r.t. its input only (frozen VAE)")
+        B, H, W, C = x.shape
+        L = H * W
+        Lp = p_buf.shape[2]
+        scale = C ** -0.5
+        dev = x.device
+        dout = dout.contiguous()
+        do, _, _ = bw.linear_bwd(o.view(B * L, C), pk["wo"], ops.cast_f16(dout).view(B * L, C), need_dw=False)
+        do = do.view(B, L, C)
+        v = ops.linear(hn.view(B * L, C), pk["wv"], pk["bv"]).view(B, L, C)            # recomputed (forward keeps V^T)
+        dqk = torch.empty((B, L, 2 * C), dtype=F16, device=dev)
+        dv = torch.empty((B, L, C), dtype=F16, device=dev)
+        for b in range(B):
+            q_b, k_b = qk[b, :, :C], qk[b, :, C:]
+            dp = torch.zeros((L, Lp), dtype=F32, device=dev)
+            ops.linear(do[b], v[b], out=dp[:, :L], out_dtype=F32)
+            ds = ops.softmax_bwd_rows(p_buf[b], dp, scale, cols=L)                     # [L, Lp] fp16, padding 0
+            del dp
+            ops.linear(ds, ops.transpose_rows(k_b), out=dqk[b, :, :C])                 # K^T [C, L8], L8 == Lp
+            dst = ops.transpose_rows(ds[:, :L])                                         # [L, L8]
+            ops.linear(dst, ops.transpose_rows(q_b), out=dqk[b, :, C:])
+            pt = ops.transpose_rows(p_buf[b][:, :L])
+            ops.linear(pt, ops.transpose_rows(do[b]), out=dv[b])
+        dhn, _, _ = bw.linear_bwd(hn.view(B * L, C), pk["wqk"], dqk.view(B * L, 2 * C), need_dw=False)
+        dhn, _, _ = bw.linear_bwd(hn.view(B * L, C), pk["wv"], dv.view(B * L, C), need_dw=False, da_add=dhn)
+        (dx,), _, _ = ops.group_norm_bwd([x], dhn.view(B, H, W, C), mr, pk["g"], pk["b"], m.groups, False, [dout], F32)
+        return None, None, dx
+
+
+def vae_attention(m, x):
+    box = {}
+    return _attach(_VAEAttentionFn.apply(m, box, x), box)
+
+
+# --------------------------------------------------------------- latent -> decoder input, post-ops and losses
+class _PointwiseFn(torch.autograd.Function):
+    """Conv1x1Small (post_quant_conv with the x0 / scaling-factor coefficients folded in): out = W (a1 * x) + b."""
+
+    @staticmethod
+    def forward(ctx, conv, a1, x):
+        w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).to(F32).contiguous()
+        b = conv.bias.detach().to(F32).contiguous()
+        ctx.w, ctx.a1 = w, a1
+        return ops.pointwise_nchw(x.float().contiguous(), a1, w, b, cin=conv.in_channels)
+
+    @staticmethod
+    def backward(ctx, dout):
+        wt = ctx.w.t().contiguous()
+        zero = torch.zeros((wt.shape[0],), dtype=F32, device=dout.device)
+        return None, None, ops.pointwise_nchw(dout.float().contiguous(), ctx.a1, wt, zero, cin=wt.shape[1])
+
+
+def pointwise(conv, x, a1):
+    return _PointwiseFn.apply(conv, a1, x)
+
+
+class _DecodePostFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, normals):
+        x = x.float().contiguous()
+        ctx.saved, ctx.normals = (x,), normals
+        return ops.decode_post(x, normals=normals, training=True)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return ops.decode_post_bwd(ctx.saved[0], dout.float().contiguous(), ctx.normals), None
+
+
+def decode_post(x, normals):
+    return _DecodePostFn.apply(x, normals)
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, est, target, mask, normals):
+        ctx.saved, ctx.normals = (est, target, mask), normals
+        return (ops.angular_loss if normals else ops.ssi_loss)(est, target, mask)
+
+    @staticmethod
+    def backward(ctx, gout):
+        est, target, mask = ctx.saved
+        fn = ops.angular_loss_bwd if ctx.normals else ops.ssi_loss_bwd
+        return fn(est, target, mask, gout).view_as(est), None, None, None
+
+
+def task_loss(est, target, mask, normals):
+    return _LossFn.apply(est, target, mask, normals)

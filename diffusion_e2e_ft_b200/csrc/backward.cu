@@ -403,6 +403,153 @@ __global__ void geglu_bwd_kernel(const __half* __restrict__ h, const __half* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------- loss backward
+// Scale-and-shift-invariant L1 (training/util/loss.py:13-47) differentiated THROUGH the per-image least-squares
+// (s, t), as torch.autograd does in the reference.  ws (zeroed double [7*B]): [5b..5b+4] = moments
+// (sum m p p, sum m p, sum m, sum m p y, sum m y), [5B+2b..] = (sum m sgn(r), sum m sgn(r) p), r = s p + t - y.
+__device__ __forceinline__ double bw_warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void ssi_fit(const double* ws, int b, double& s, double& t, double& det) {
+  const double a00 = ws[b * 5 + 0], a01 = ws[b * 5 + 1], a11 = ws[b * 5 + 2], b0 = ws[b * 5 + 3], b1 = ws[b * 5 + 4];
+  det = a00 * a11 - a01 * a01;
+  s = 0.0; t = 0.0;
+  if (det > 0) { s = (a11 * b0 - a01 * b1) / det; t = (-a01 * b0 + a00 * b1) / det; }
+}
+__global__ void ssi_bwd_moments_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                       const uint8_t* __restrict__ mask, long long HW, double* __restrict__ ws) {
+  const int b = blockIdx.y;
+  const float* p = pred + (long long)b * HW;
+  const float* y = tgt + (long long)b * HW;
+  const uint8_t* m = mask + (long long)b * HW;
+  double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    if (m[i]) {
+      const double pv = p[i], yv = y[i];
+      a00 += pv * pv; a01 += pv; a11 += 1.0; b0 += pv * yv; b1 += yv;
+    }
+  }
+  a00 = bw_warp_sum_d(a00); a01 = bw_warp_sum_d(a01); a11 = bw_warp_sum_d(a11); b0 = bw_warp_sum_d(b0); b1 = bw_warp_sum_d(b1);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&ws[b * 5 + 0], a00); atomicAdd(&ws[b * 5 + 1], a01); atomicAdd(&ws[b * 5 + 2], a11);
+    atomicAdd(&ws[b * 5 + 3], b0);  atomicAdd(&ws[b * 5 + 4], b1);
+  }
+}
+__global__ void ssi_bwd_sign_sums_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                         const uint8_t* __restrict__ mask, long long HW, int B, double* __restrict__ ws) {
+  const int b = blockIdx.y;
+  double s, t, det;
+  ssi_fit(ws, b, s, t, det);
+  const float sf = (float)s, tf = (float)t;                   // the forward evaluates the residual in fp32
+  const float* p = pred + (long long)b * HW;
+  const float* y = tgt + (long long)b * HW;
+  const uint8_t* m = mask + (long long)b * HW;
+  double g0 = 0, g1 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x)
+    if (m[i]) {
+      const float r = sf * p[i] + tf - y[i];
+      const double sg = (r > 0.f) - (r < 0.f);
+      g0 += sg; g1 += sg * (double)p[i];
+    }
+  g0 = bw_warp_sum_d(g0); g1 = bw_warp_sum_d(g1);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&ws[5 * B + 2 * b], g0); atomicAdd(&ws[5 * B + 2 * b + 1], g1); }
+}
+__global__ void ssi_bwd_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                    const uint8_t* __restrict__ mask, long long HW, int B, const double* __restrict__ ws,
+                                    const float* __restrict__ gscale, float* __restrict__ dpred) {
+  const int b = blockIdx.y;
+  double s, t, det;
+  ssi_fit(ws, b, s, t, det);
+  double N = 0;
+  for (int i = 0; i < B; ++i) N += ws[i * 5 + 2];
+  const double a01 = ws[b * 5 + 1], a11 = ws[b * 5 + 2], b0 = ws[b * 5 + 3], b1 = ws[b * 5 + 4];
+  const double G0 = ws[5 * B + 2 * b] / N, G1 = ws[5 * B + 2 * b + 1] / N;
+  const double up = (double)gscale[0];
+  const float sf = (float)s, tf = (float)t;
+  const float* p = pred + (long long)b * HW;
+  const float* y = tgt + (long long)b * HW;
+  const uint8_t* m = mask + (long long)b * HW;
+  float* o = dpred + (long long)b * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    double g = 0.0;
+    if (m[i] && N > 0) {
+      const double pv = p[i], yv = y[i];
+      const float r = sf * p[i] + tf - y[i];
+      g = ((r > 0.f) - (r < 0.f)) * s / N;
+      if (det > 0) {
+        const double ddet = 2.0 * pv * a11 - 2.0 * a01;
+        const double dns = a11 * yv - b1;
+        const double dnt = -b0 - a01 * yv + 2.0 * pv * b1;
+        g += (G1 * (dns - s * ddet) + G0 * (dnt - t * ddet)) / det;
+      }
+    }
+    o[i] = (float)(up * g);
+  }
+}
+
+// AngularLoss (loss.py:51-67): mean over the mask of acos(clamp(<p, y>, -1, 1)); ws (zeroed double [1]) = count.
+__global__ void mask_count_kernel(const uint8_t* __restrict__ mask, long long n, double* __restrict__ ws) {
+  double c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c += mask[i] ? 1.0 : 0.0;
+  c = bw_warp_sum_d(c);
+  if ((threadIdx.x & 31) == 0) atomicAdd(ws, c);
+}
+__global__ void angular_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                   const uint8_t* __restrict__ mask, long long HW, const double* __restrict__ ws,
+                                   const float* __restrict__ gscale, float* __restrict__ dpred) {
+  const int b = blockIdx.y;
+  const float* p = pred + (long long)b * 3 * HW;
+  const float* y = tgt + (long long)b * 3 * HW;
+  const uint8_t* m = mask + (long long)b * HW;
+  float* o = dpred + (long long)b * 3 * HW;
+  const float k = (float)((double)gscale[0] / ws[0]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    float g = 0.f;
+    if (m[i]) {
+      const float d = p[i] * y[i] + p[HW + i] * y[HW + i] + p[2 * HW + i] * y[2 * HW + i];
+      if (d > -1.0f && d < 1.0f) g = -k * rsqrtf(1.0f - d * d);
+    }
+    o[i] = g * y[i];
+    o[HW + i] = g * y[HW + i];
+    o[2 * HW + i] = g * y[2 * HW + i];
+  }
+}
+
+// decode_post training modes (train.py:532-540) backward.  mode 2: est = clamp(mean_c x, -1, 1);
+// mode 3: est_c = clamp(x_c / (|x| + 1e-5), -1, 1).
+__global__ void decode_post_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, long long HW,
+                                       int mode, float* __restrict__ dx) {
+  const int n = blockIdx.y;
+  const float* xb = x + (long long)n * 3 * HW;
+  float* ob = dx + (long long)n * 3 * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    const float a = xb[p], b = xb[HW + p], c = xb[2 * HW + p];
+    if (mode == 2) {
+      const float m = (a + b + c) / 3.0f;
+      const float g = (m >= -1.0f && m <= 1.0f) ? dout[(long long)n * HW + p] / 3.0f : 0.f;
+      ob[p] = g; ob[HW + p] = g; ob[2 * HW + p] = g;
+    } else {
+      const float* db = dout + (long long)n * 3 * HW;
+      const float nrm = sqrtf(a * a + b * b + c * c);
+      const float inv = 1.0f / (nrm + 1e-5f);
+      const float u0 = a * inv, u1 = b * inv, u2 = c * inv;
+      const float g0 = (u0 >= -1.f && u0 <= 1.f) ? db[p] : 0.f;
+      const float g1 = (u1 >= -1.f && u1 <= 1.f) ? db[HW + p] : 0.f;
+      const float g2 = (u2 >= -1.f && u2 <= 1.f) ? db[2 * HW + p] : 0.f;
+      // u = x / (|x| + eps):  du_c/dx_k = delta_ck * inv - x_c x_k * inv^2 / |x|
+      const float dot = g0 * a + g1 * b + g2 * c;
+      const float k = nrm > 0.f ? dot * inv * inv / nrm : 0.f;
+      ob[p] = g0 * inv - a * k;
+      ob[HW + p] = g1 * inv - b * k;
+      ob[2 * HW + p] = g2 * inv - c * k;
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -586,5 +733,46 @@ extern "C" int b200_geglu_bwd(const void* h, const void* g, long long ld_hg, con
   geglu_bwd_kernel<<<bw_grid1d(rows * inner, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)h, (const __half*)g, ld_hg, (const __half*)dy, rows, inner, (__half*)dh, (__half*)dg, ld_d);
   B200_CHECK_LAUNCH("geglu_bwd_kernel");
+  return 0;
+}
+
+static dim3 bw_loss_grid(long long HW, int B) {
+  long long g = (HW + 256 * 8 - 1) / (256 * 8);
+  long long cap = (long long)sm_count() * 4 / (B > 0 ? B : 1) + 1;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return dim3((unsigned)g, B);
+}
+
+extern "C" int b200_ssi_loss_bwd(const float* pred, const float* target, const unsigned char* mask, int B,
+                                 long long HW, double* workspace, const float* grad_out, float* dpred, void* stream) {
+  B200_CHECK_ARG(pred && target && mask && workspace && grad_out && dpred && B > 0 && HW > 0,
+                 "b200_ssi_loss_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid = bw_loss_grid(HW, B);
+  ssi_bwd_moments_kernel<<<grid, 256, 0, st>>>(pred, target, mask, HW, workspace);
+  ssi_bwd_sign_sums_kernel<<<grid, 256, 0, st>>>(pred, target, mask, HW, B, workspace);
+  ssi_bwd_grad_kernel<<<grid, 256, 0, st>>>(pred, target, mask, HW, B, workspace, grad_out, dpred);
+  B200_CHECK_LAUNCH("ssi_loss_bwd kernels");
+  return 0;
+}
+
+extern "C" int b200_angular_loss_bwd(const float* pred, const float* target, const unsigned char* mask, int B,
+                                     long long HW, double* workspace, const float* grad_out, float* dpred,
+                                     void* stream) {
+  B200_CHECK_ARG(pred && target && mask && workspace && grad_out && dpred && B > 0 && HW > 0,
+                 "b200_angular_loss_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  mask_count_kernel<<<bw_grid1d((long long)B * HW, 256), 256, 0, st>>>(mask, (long long)B * HW, workspace);
+  angular_bwd_kernel<<<bw_loss_grid(HW, B), 256, 0, st>>>(pred, target, mask, HW, workspace, grad_out, dpred);
+  B200_CHECK_LAUNCH("angular_loss_bwd kernels");
+  return 0;
+}
+
+extern "C" int b200_decode_post_bwd(const float* x, const float* dout, int NB, long long HW, int mode, float* dx,
+                                    void* stream) {
+  B200_CHECK_ARG(x && dout && dx && NB > 0 && HW > 0 && (mode == 2 || mode == 3), "b200_decode_post_bwd: bad arguments");
+  decode_post_bwd_kernel<<<bw_loss_grid(HW, NB), 256, 0, (cudaStream_t)stream>>>(x, dout, HW, mode, dx);
+  B200_CHECK_LAUNCH("decode_post_bwd_kernel");
   return 0;
 }

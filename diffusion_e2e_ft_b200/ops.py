@@ -616,3 +616,46 @@ def geglu_bwd(hg, dy):
     _ck(_lib.load().b200_geglu_bwd(_p(hg), _p(hg[:, inner:]), 2 * inner, _p(dy), rows, inner, _p(d), _p(d[:, inner:]),
                                    2 * inner, _stream()), "b200_geglu_bwd")
     return d
+
+
+@_timed("loss")
+def ssi_loss_bwd(pred, target, mask, grad_out):
+    """d ssi_loss / d pred * grad_out (0-d fp32 device tensor) -> fp32, shape of pred."""
+    _need_cuda(pred, target, mask, grad_out)
+    B = pred.shape[0]
+    hw = pred.numel() // B
+    p, t = pred.float().contiguous(), target.float().contiguous()
+    m = mask.reshape(B, -1).to(torch.uint8).contiguous()
+    ws = torch.zeros(7 * B, dtype=torch.float64, device=pred.device)
+    out = torch.empty(p.shape, dtype=F32, device=pred.device)
+    go = grad_out.detach().to(F32).reshape(1).contiguous()
+    _ck(_lib.load().b200_ssi_loss_bwd(_p(p), _p(t), _p(m), B, hw, _p(ws), _p(go), _p(out), _stream()), "b200_ssi_loss_bwd")
+    return out
+
+
+@_timed("loss")
+def angular_loss_bwd(pred, target, mask, grad_out):
+    _need_cuda(pred, target, mask, grad_out)
+    B = pred.shape[0]
+    hw = pred.numel() // (3 * B)
+    p, t = pred.float().contiguous(), target.float().contiguous()
+    m = mask.reshape(B, -1).to(torch.uint8).contiguous()
+    ws = torch.zeros(1, dtype=torch.float64, device=pred.device)
+    out = torch.empty(p.shape, dtype=F32, device=pred.device)
+    go = grad_out.detach().to(F32).reshape(1).contiguous()
+    _ck(_lib.load().b200_angular_loss_bwd(_p(p), _p(t), _p(m), B, hw, _p(ws), _p(go), _p(out), _stream()),
+        "b200_angular_loss_bwd")
+    return out
+
+
+@_timed("misc")
+def decode_post_bwd(x, dout, normals=False):
+    """Backward of decode_post(..., training=True): x [NB,3,H,W] fp32 decoder output, dout the gradient of the
+    estimate ([NB,1,H,W] depth / [NB,3,H,W] normals)."""
+    _need_cuda(x, dout)
+    assert x.dtype == F32 and x.is_contiguous() and dout.dtype == F32 and dout.is_contiguous()
+    NB, _, H, W = x.shape
+    dx = torch.empty_like(x)
+    _ck(_lib.load().b200_decode_post_bwd(_p(x), _p(dout), NB, H * W, 3 if normals else 2, _p(dx), _stream()),
+        "b200_decode_post_bwd")
+    return dx

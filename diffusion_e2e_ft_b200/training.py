@@ -3,9 +3,10 @@
     rgb -> VAE.encode * scaling -> UNet(t = T-1, zeros noise, ctx[B,77,1024]) -> x0 (v-prediction)
         -> / scaling -> VAE.decode -> depth: mean_c, clamp | normals: normalise, clamp -> SSI / angular loss
 
-Everything runs in libb200_e2eft.so kernels (incl. the losses).  The BACKWARD (conv dgrad/wgrad, attention
-backward, GN/LN backward, AdamW, NCCL gradient all-reduce) is not implemented in round 1: this module is
-inference-mode only and exists so the loss value of a training micro-step can be checked against the oracle.
+Everything runs in libb200_e2eft.so kernels (incl. the losses).  `e2e_ft_forward` is the no-grad forward (loss value
+only); `e2e_ft_loss` is the differentiable one: `e2e_ft_loss(...)[0].backward()` fills `.grad` of the UNet
+parameters through the autograd blocks (autograd_blocks.py), `optimizer_step_` then does the gradient all-reduce,
+clipping and AdamW on flat buffers.
 """
 import math
 
@@ -36,6 +37,31 @@ def e2e_ft_forward(unet, vae, scheduler, rgb, ground_truth, val_mask, empty_enco
     else:
         raise ValueError(f"Unknown modality {modality}")
     return loss, est
+
+
+LOSS_SCALE = 1024.0       # static loss scale: incoming gradients are fp16 GEMM operands in the backward pass
+
+
+def e2e_ft_loss(unet, vae, scheduler, rgb, ground_truth, val_mask, empty_encoding, modality="depth"):
+    """Differentiable training micro-step (training/train.py:469-556).  Returns (loss, estimate); call
+    `(loss * LOSS_SCALE).backward()` and divide the gradients by LOSS_SCALE (or pass `grad_unscale` to the
+    optimizer step).  VAE encode runs without grad (frozen, train.py:473 under no_grad)."""
+    from . import autograd_blocks as ab
+    B = rgb.shape[0]
+    with torch.no_grad():
+        rgb_latents = vae.encode_scaled_mean(rgb)
+    T = scheduler.config["num_train_timesteps"]
+    t = T - 1
+    ctx = empty_encoding.to(rgb.device).repeat(B, 1, 1)
+    model_pred = unet(torch.cat((rgb_latents, torch.zeros_like(rgb_latents)), dim=1), t, ctx, return_dict=False)[0]
+    a_t = float(scheduler.alphas_cumprod[t])
+    assert scheduler.config["prediction_type"] == "v_prediction"
+    dec = vae.decode_from_prediction(model_pred, -math.sqrt(1.0 - a_t))
+    normals = modality == "normals"
+    if modality not in ("depth", "normals"):
+        raise ValueError(f"Unknown modality {modality}")
+    est = ab.decode_post(dec, normals)
+    return ab.task_loss(est, ground_truth, val_mask, normals), est
 
 
 def allreduce_mean_(flat_grad, group=None):

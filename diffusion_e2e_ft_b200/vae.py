@@ -87,8 +87,7 @@ class _UpDecoderBlock(nn.Module):
 
 
 def _check_input(x, who):
-    if not x.is_cuda:
-        raise RuntimeError(f"{who} runs on sm_100a only (no CPU fallback)")
+    ops._need_cuda(x)                                  # sm_100a only, no CPU fallback
     if torch.is_grad_enabled() and x.requires_grad:
         raise NotImplementedError(f"backward through {who} is not implemented yet; wrap in torch.no_grad()")
 
@@ -147,6 +146,8 @@ class Decoder(nn.Module):
         self._out = ConvOutSmall(self.conv_norm_out, self.conv_out)
 
     def forward(self, z):
+        if torch.is_grad_enabled() and z.requires_grad:
+            return self._forward_train(z)
         _check_input(z, "B200AutoencoderKL.decoder")
         sdt = self.stream_dtype
         h = self._in.run(z if z.dtype in (F16, F32) else z.float(), sdt)
@@ -158,6 +159,29 @@ class Decoder(nn.Module):
                 h = blk.upsamplers[0].run(h, None, sdt)
         out = self._out.run(h)
         return out if out.dtype == z.dtype else out.to(z.dtype)
+
+
+def _decoder_forward_train(self, z):
+    """Differentiable decoder (row a10): same graph as `Decoder.forward` on the autograd blocks.  With the VAE
+    frozen (training/train.py:323-326) only the data gradient is produced."""
+    from . import autograd_blocks as ab
+    if self.stream_dtype != F32:
+        raise NotImplementedError("training runs with the fp32 residual stream (stream_dtype=torch.float32)")
+    h = ab.conv_in(self._in, z if z.dtype in (F16, F32) else z.float())
+    mb = self.mid_block
+    h = ab.resnet(mb.resnets[0], h)
+    h = ab.vae_attention(mb.attentions[0], h)
+    h = ab.resnet(mb.resnets[1], h)
+    for blk in self.up_blocks:
+        for i, r in enumerate(blk.resnets):
+            h = ab.resnet(r, h, f16_copy=(i == len(blk.resnets) - 1 and blk.upsamplers is not None))
+        if blk.upsamplers is not None:
+            h = ab.upsample(blk.upsamplers[0], h)
+    out = ab.conv_out(self._out, h)
+    return out if out.dtype == z.dtype else out.to(z.dtype)
+
+
+Decoder._forward_train = _decoder_forward_train
 
 
 class Conv1x1Small(nn.Conv2d):
@@ -215,5 +239,10 @@ class B200AutoencoderKL(nn.Module):
         """x0 = c_noisy*noisy + c_out*model_out (scheduler closed form), / scaling_factor,
         post_quant_conv, decoder  (marigold_pipeline.py:457-465, 513-516)."""
         s = 1.0 / self.config["scaling_factor"]
+        if torch.is_grad_enabled() and model_out.requires_grad:
+            from . import autograd_blocks as ab
+            if noisy is not None and c_noisy != 0.0:
+                raise NotImplementedError("differentiable decode supports the x_t = 0 recipe (noise_type zeros) only")
+            return self.decoder(ab.pointwise(self.post_quant_conv, model_out, c_out * s))
         z = self.post_quant_conv(model_out, scale_in=c_out * s, x2=noisy, scale_in2=c_noisy * s)
         return self.decoder(z)

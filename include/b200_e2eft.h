@@ -209,6 +209,16 @@ int b200_act_bwd(const void* x, const void* dy, long long n, int act, void* dx, 
 int b200_geglu_bwd(const void* h, const void* g, long long ld_hg, const void* dy, long long rows, int inner, void* dh,
                    void* dg, long long ld_d, void* stream);
 
+/* Loss / post-op backward of the fine-tuning step (training/train.py:532-556, training/util/loss.py):
+ * d(loss)/d(pred) * grad_out[0] (device scalar: the upstream gradient, i.e. the loss scale).  The SSI gradient
+ * flows through the per-image least-squares scale/shift, as torch.autograd does in the reference.
+ * workspace: zeroed doubles, 7*B (ssi) / 1 (angular).  decode_post_bwd: modes 2 (depth) / 3 (normals). */
+int b200_ssi_loss_bwd(const float* pred, const float* target, const unsigned char* mask, int B, long long HW,
+                      double* workspace, const float* grad_out, float* dpred, void* stream);
+int b200_angular_loss_bwd(const float* pred, const float* target, const unsigned char* mask, int B, long long HW,
+                          double* workspace, const float* grad_out, float* dpred, void* stream);
+int b200_decode_post_bwd(const float* x, const float* dout, int NB, long long HW, int mode, float* dx, void* stream);
+
 /* fp32 <-> fp16 casts / layout helpers used at module boundaries. */
 int b200_cast_f32_to_f16(const float* x, void* y, long long n, void* stream);
 int b200_nhwc_to_nchw_f32(const void* x, int in_f32, int NB, int C, long long HW, float* y, void* stream);

@@ -214,7 +214,65 @@ def check_attention_bwd(B=2, T=192, Tk=192, heads=2, fused_qkv=True, seed=23):
     return _worst([(dq, back(qr.grad)), (dk, back(kr.grad)), (dv, back(vr.grad))]), 3e-3
 
 
+# ------------------------------------------------------------------------------------------ losses / post-op
+def _ssi_ref(p, y, m):
+    mf = m.float()
+    a00, a01, a11 = (mf * p * p).sum((1, 2, 3)), (mf * p).sum((1, 2, 3)), mf.sum((1, 2, 3))
+    b0, b1 = (mf * p * y).sum((1, 2, 3)), (mf * y).sum((1, 2, 3))
+    det = a00 * a11 - a01 * a01
+    s = (a11 * b0 - a01 * b1) / det
+    t = (-a01 * b0 + a00 * b1) / det
+    r = s.view(-1, 1, 1, 1) * p + t.view(-1, 1, 1, 1) - y
+    return r.abs()[m].mean()
+
+
+def check_ssi_loss_bwd(B=3, H=40, W=56, seed=41):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    p = (torch.rand(B, 1, H, W, generator=g) * 2 - 1).to(DEV)
+    y = (torch.rand(B, 1, H, W, generator=g) * 9 + 0.5).to(DEV)
+    m = (torch.rand(B, 1, H, W, generator=g) > 0.3).to(DEV)
+    go = torch.tensor(512.0, device=DEV)
+    got = ops.ssi_loss_bwd(p, y, m, go)
+    torch.cuda.synchronize()
+    pr = p.double().requires_grad_(True)
+    (_ssi_ref(pr, y.double(), m) * 512.0).backward()
+    return rel_l2(got, pr.grad), 1e-4
+
+
+def check_angular_loss_bwd(B=2, H=40, W=56, seed=43):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    p = F.normalize(torch.randn(B, 3, H, W, generator=g), dim=1).to(DEV)
+    y = F.normalize(torch.randn(B, 3, H, W, generator=g), dim=1).to(DEV)
+    m = (torch.rand(B, 1, H, W, generator=g) > 0.3).to(DEV)
+    go = torch.tensor(64.0, device=DEV)
+    got = ops.angular_loss_bwd(p, y, m, go)
+    torch.cuda.synchronize()
+    pr = p.double().requires_grad_(True)
+    (torch.acos((pr * y.double()).sum(1).clamp(-1, 1))[m[:, 0]].mean() * 64.0).backward()
+    return rel_l2(got, pr.grad), 1e-4
+
+
+def check_decode_post_bwd(normals, B=2, H=24, W=40, seed=45):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(B, 3, H, W, generator=g) * (0.4 if normals else 0.8)).to(DEV)
+    dy = torch.randn(B, 3 if normals else 1, H, W, generator=g).to(DEV)
+    got = ops.decode_post_bwd(x, dy, normals)
+    torch.cuda.synchronize()
+    xr = x.clone().requires_grad_(True)
+    if normals:
+        est = (xr / (xr.norm(dim=1, keepdim=True) + 1e-5)).clamp(-1, 1)
+    else:
+        est = xr.mean(1, keepdim=True).clamp(-1, 1)
+    (est * dy).sum().backward()
+    fwd = rel_l2(ops.decode_post(x, normals=normals, training=True), est)
+    return rel_l2(got, xr.grad) + fwd, 1e-5
+
+
 BWD_CHECKS = {
+    "bwd_ssi_loss": check_ssi_loss_bwd,
+    "bwd_angular_loss": check_angular_loss_bwd,
+    "bwd_decode_post_depth": lambda: check_decode_post_bwd(False),
+    "bwd_decode_post_normals": lambda: check_decode_post_bwd(True),
     "bwd_gather_transpose": lambda: check_gather_planar(),
     "bwd_gather_f32_shift": lambda: check_gather_planar(in_f32=True, off=(-1, 1)),
     "bwd_gather_stride2": lambda: check_gather_planar(stride=2, off=(-1, -1)),

@@ -261,12 +261,80 @@ def nhwc_to_nchw_f32(x):
     return x.float().permute(0, 3, 1, 2).contiguous()
 
 
+def pointwise_nchw(in1, a1, wm, bias, in2=None, a2=0.0, cin=None):
+    cin = cin or wm.shape[1]
+    x = a1 * in1[:, :cin].float()
+    if in2 is not None:
+        x = x + a2 * in2[:, :cin].float()
+    return torch.einsum("oc,nchw->nohw", wm[:, :cin].float(), x) + bias.float()[None, :, None, None]
+
+
+def decode_post(x, normals=False, sign=1.0, training=False):
+    if not normals:
+        m = x.mean(1, keepdim=True).clamp(-1, 1)
+        return m if training else (m + 1) / 2
+    u = sign * x / (x.norm(dim=1, keepdim=True) + 1e-5)
+    return u.clamp(-1, 1) if training else u
+
+
+def _ssi(pred, target, mask):
+    m = mask.reshape(pred.shape[0], -1).float()
+    p, y = pred.reshape(pred.shape[0], -1).float(), target.reshape(pred.shape[0], -1).float()
+    a00, a01, a11 = (m * p * p).sum(1), (m * p).sum(1), m.sum(1)
+    b0, b1 = (m * p * y).sum(1), (m * y).sum(1)
+    det = a00 * a11 - a01 * a01
+    ok = det > 0
+    safe = torch.where(ok, det, torch.ones_like(det))
+    s = torch.where(ok, (a11 * b0 - a01 * b1) / safe, torch.zeros_like(det))
+    t = torch.where(ok, (-a01 * b0 + a00 * b1) / safe, torch.zeros_like(det))
+    r = (s[:, None] * p + t[:, None] - y).abs() * m
+    return r.sum() / m.sum()
+
+
+def _angular(pred, target, mask):
+    d = (pred.float() * target.float()).sum(1).clamp(-1, 1)
+    m = mask[:, 0].float()
+    return (torch.acos(d) * m).sum() / m.sum()
+
+
+def ssi_loss(pred, target, mask):
+    return _ssi(pred, target, mask)
+
+
+def angular_loss(pred, target, mask):
+    return _angular(pred, target, mask)
+
+
+def _loss_bwd(fn, pred, target, mask, grad_out):
+    p = pred.detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        (fn(p, target, mask) * grad_out.detach().float()).backward()
+    return p.grad
+
+
+def ssi_loss_bwd(pred, target, mask, grad_out):
+    return _loss_bwd(_ssi, pred, target, mask, grad_out)
+
+
+def angular_loss_bwd(pred, target, mask, grad_out):
+    return _loss_bwd(_angular, pred, target, mask, grad_out)
+
+
+def decode_post_bwd(x, dout, normals=False):
+    xr = x.detach().requires_grad_(True)
+    with torch.enable_grad():
+        (decode_post(xr, normals=normals, training=True) * dout).sum().backward()
+    return xr.grad
+
+
 _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm_mean_rstd=group_norm_mean_rstd,
                  group_norm_bwd=group_norm_bwd, layer_norm=layer_norm, layer_norm_bwd=layer_norm_bwd,
                  attention_d64=attention_d64, softmax_rows=softmax_rows, softmax_bwd_rows=softmax_bwd_rows,
                  gather_planar=gather_planar, col_sum=col_sum, act_bwd=act_bwd, geglu_bwd=geglu_bwd,
                  cast_f16=cast_f16, im2col3x3=im2col3x3, conv3x3_small_cout=conv3x3_small_cout,
-                 timestep_embedding=timestep_embedding, nhwc_to_nchw_f32=nhwc_to_nchw_f32)
+                 timestep_embedding=timestep_embedding, nhwc_to_nchw_f32=nhwc_to_nchw_f32,
+                 pointwise_nchw=pointwise_nchw, decode_post=decode_post, ssi_loss=ssi_loss, angular_loss=angular_loss,
+                 ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd)
 
 
 def install(monkeypatch):

@@ -209,3 +209,50 @@ def run_unet_backward_tiny(device="cuda:0", hw=(16, 16), ctx_tokens=77):
         den += gr.pow(2).sum().item()
     return dict(forward=rel_l2(y, yr), grad_global=(num / den) ** 0.5, grad_worst=worst, worst_name=worst_name,
                 missing=missing, n_params=len(ref))
+
+
+def run_training_step_tiny(device="cuda:0", modality="depth"):
+    """Row a10, whole micro-step: rgb -> frozen VAE encode -> UNet -> x0 -> frozen VAE decode -> post-op -> task loss,
+    then backward: gradients of every UNet parameter (engine autograd blocks) vs torch.autograd through the fp32
+    oracle graph (training/train.py:469-563)."""
+    from diffusion_e2e_ft_b200.training import LOSS_SCALE, e2e_ft_loss
+    unet_ref, vae_ref = MG.build_tiny()
+    unet, vae = engine_from_oracle(unet_ref, vae_ref, device)
+    unet.requires_grad_(True)
+    unet_ref.requires_grad_(True)
+    vae_ref.requires_grad_(False)
+    g = torch.Generator().manual_seed(13)
+    rgb = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    ctx = torch.randn(1, 77, 128, generator=g) * 0.5
+    mask = torch.rand(2, 1, 64, 64, generator=g) > 0.2
+    sched_o = OP.DDIMOneStep()
+    with torch.no_grad():
+        lat = OP.encode_rgb(vae_ref, rgb)
+    v = unet_ref(torch.cat([lat, torch.zeros_like(lat)], 1), 999, ctx.repeat(2, 1, 1)).sample
+    dec = OP.decode_latent(vae_ref, sched_o.pred_original_sample(v, 999, torch.zeros_like(lat)))
+    if modality == "depth":
+        gt = torch.rand(2, 1, 64, 64, generator=g) * 9.9 + 0.1
+        want = OP.ssi_loss(dec.mean(1, keepdim=True).clamp(-1, 1), gt, mask)
+    else:
+        gt = torch.nn.functional.normalize(torch.randn(2, 3, 64, 64, generator=g), dim=1)
+        est = dec / (dec.norm(dim=1, keepdim=True) + 1e-5)
+        want = OP.angular_loss(est.clamp(-1, 1), gt, mask)
+    want.backward()
+    got, _ = e2e_ft_loss(unet, vae, DDIMScheduler(), rgb.to(device), gt.to(device), mask.to(device), ctx.to(device),
+                         modality)
+    (got * LOSS_SCALE).backward()
+    ref = dict(unet_ref.named_parameters())
+    num = den = 0.0
+    worst, worst_name, missing = 0.0, None, []
+    for n, p in unet.named_parameters():
+        if p.grad is None:
+            missing.append(n)
+            continue
+        ge, gr = p.grad.detach().float().cpu() / LOSS_SCALE, ref[n].grad
+        e = rel_l2(ge, gr)
+        if e > worst and gr.norm() > 1e-3 * den ** 0.5:          # ignore parameters with a vanishing gradient
+            worst, worst_name = e, n
+        num += (ge - gr).pow(2).sum().item()
+        den += gr.pow(2).sum().item()
+    return dict(loss_engine=got.item(), loss_oracle=want.item(), loss_rel=abs(got.item() - want.item()) / abs(want.item()),
+                grad_global=(num / den) ** 0.5, grad_worst=worst, worst_name=worst_name, missing=missing)

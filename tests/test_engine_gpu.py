@@ -91,3 +91,16 @@ def test_unet_backward_matches_oracle_autograd():
     assert not r["missing"], r["missing"]
     assert r["forward"] <= 3e-3, r
     assert r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2, r
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("modality,tol", [("depth", 3e-2), ("normals", 6e-2)])
+def test_training_micro_step_gradients_match_oracle(modality, tol):
+    """Whole differentiable micro-step (frozen VAE encode -> UNet -> x0 -> frozen VAE decode -> post-op -> task loss)
+    with `backward()`: UNet parameter gradients vs torch.autograd through the fp32 oracle.  The tolerance is wider
+    than for the UNet alone: fp16 operands through the VAE decoder backward as well, and both losses are
+    non-smooth (sign of the L1 residual, clamp / acos), so the 2e-3 forward difference flips a few pixels."""
+    r = EC.run_training_step_tiny(modality=modality)
+    assert not r["missing"], r["missing"]
+    assert r["loss_rel"] <= 3e-3, r
+    assert r["grad_global"] <= tol and r["grad_worst"] <= 3 * tol, r

@@ -20,3 +20,11 @@ def test_unet_backward_wiring_matches_oracle_autograd(emulated):
     assert r["n_params"] == 686
     assert r["forward"] <= 3e-3, r
     assert r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2, r
+
+
+@pytest.mark.parametrize("modality,tol", [("depth", 3e-2), ("normals", 6e-2)])
+def test_training_micro_step_wiring(emulated, modality, tol):
+    r = EC.run_training_step_tiny(device="cpu", modality=modality)
+    assert not r["missing"], r["missing"]
+    assert r["loss_rel"] <= 3e-3, r
+    assert r["grad_global"] <= tol and r["grad_worst"] <= 3 * tol, r
