@@ -27,11 +27,13 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* _
 // min(1, max_norm / (||g|| + 1e-6)) read from the device (no host sync between norm and step).
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
-                             float wd, float bc1, float bc2, const double* __restrict__ gnorm_sq, float max_norm) {
-  float clip = 1.0f;
+                             float wd, float bc1, float bc2, const double* __restrict__ gnorm_sq, float max_norm,
+                             float unscale) {
+  // `unscale` = 1 / loss scale: the buffer holds S * g; the norm (of S * g) and the gradient are brought back first
+  float clip = unscale;
   if (gnorm_sq != nullptr && max_norm > 0.f) {
-    const float nrm = (float)sqrt(*gnorm_sq);
-    clip = fminf(1.0f, max_norm / (nrm + 1e-6f));
+    const float nrm = (float)sqrt(*gnorm_sq) * unscale;
+    clip = unscale * fminf(1.0f, max_norm / (nrm + 1e-6f));
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * clip;
@@ -57,15 +59,24 @@ extern "C" int b200_sumsq(const float* x, long long n, double* out, void* stream
   return 0;
 }
 
-extern "C" int b200_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
-                               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                               const double* grad_norm_sq, float max_grad_norm, void* stream) {
-  B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "b200_adamw_step: bad arguments");
+extern "C" int b200_adamw_step_scaled(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                      float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                      const double* grad_norm_sq, float max_grad_norm, float grad_unscale,
+                                      void* stream) {
+  B200_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1 && grad_unscale > 0.f,
+                 "b200_adamw_step: bad arguments");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
   long long g = (n + 255) / 256;
   long long cap = (long long)sm_count() * 8;
   adamw_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, (cudaStream_t)stream>>>(
-      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_norm_sq, max_grad_norm);
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_norm_sq, max_grad_norm, grad_unscale);
   B200_CHECK_LAUNCH("adamw_kernel");
   return 0;
+}
+
+extern "C" int b200_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                               const double* grad_norm_sq, float max_grad_norm, void* stream) {
+  return b200_adamw_step_scaled(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step,
+                                grad_norm_sq, max_grad_norm, 1.0f, stream);
 }

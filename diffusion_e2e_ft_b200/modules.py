@@ -34,6 +34,15 @@ class ConfigDict(dict):
         self[k] = v
 
 
+_WEIGHTS_EPOCH = [0]
+
+
+def bump_weights_epoch():
+    """Invalidate every packed-weight cache: called after an optimizer kernel has updated the parameters through
+    their flat buffer (a raw device write that torch's per-tensor version counters do not see)."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
 class Packed:
     """Cache of derived (packed fp16 / fp32-contiguous) tensors keyed on parameter identity+version."""
 
@@ -42,7 +51,7 @@ class Packed:
         self._val = None
 
     def get(self, params, build):
-        key = tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in params)
+        key = (_WEIGHTS_EPOCH[0],) + tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in params)
         if key != self._key:
             with torch.no_grad():
                 self._val = build()

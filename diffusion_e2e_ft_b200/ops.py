@@ -436,14 +436,16 @@ def grad_norm_sq(flat_grad):
 
 @_timed("optim")
 def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
-               grad_norm_sq_t=None, max_grad_norm=0.0):
-    """Fused clip_grad_norm_ + AdamW on flat fp32 buffers, in place (training/train.py:346-353,564-566)."""
+               grad_norm_sq_t=None, max_grad_norm=0.0, grad_unscale=1.0):
+    """Fused clip_grad_norm_ + AdamW on flat fp32 buffers, in place (training/train.py:346-353,564-566).
+    `grad_unscale` = 1 / loss scale when `grad` (and `grad_norm_sq_t`) hold loss-scaled gradients."""
     _need_cuda(param, grad, exp_avg, exp_avg_sq)
     for t in (param, grad, exp_avg, exp_avg_sq):
         assert t.dtype == F32 and t.is_contiguous() and t.numel() == param.numel()
-    _ck(_lib.load().b200_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
-                                    float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
-                                    _p(grad_norm_sq_t), float(max_grad_norm), _stream()), "b200_adamw_step")
+    _ck(_lib.load().b200_adamw_step_scaled(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
+                                           float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                           _p(grad_norm_sq_t), float(max_grad_norm), float(grad_unscale), _stream()),
+        "b200_adamw_step_scaled")
 
 
 @_timed("cast")

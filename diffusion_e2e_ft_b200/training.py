@@ -77,11 +77,63 @@ def allreduce_mean_(flat_grad, group=None):
 
 
 def optimizer_step_(flat_param, flat_grad, exp_avg, exp_avg_sq, step, lr=3e-5, weight_decay=1e-2, max_grad_norm=1.0,
-                    group=None):
+                    group=None, grad_unscale=1.0):
     """all-reduce -> clip_grad_norm_(max_grad_norm) -> AdamW, fused on the device without host syncs
-    (training/train.py:563-566 with the recipe of training/scripts/train_marigold_e2e_ft_depth.sh)."""
+    (training/train.py:563-566 with the recipe of training/scripts/train_marigold_e2e_ft_depth.sh).
+    `grad_unscale` = 1 / loss scale when the gradient buffer is loss-scaled."""
+    from .modules import bump_weights_epoch
     allreduce_mean_(flat_grad, group)
     nsq = ops.grad_norm_sq(flat_grad)
     ops.adamw_step(flat_param, flat_grad, exp_avg, exp_avg_sq, step, lr=lr, weight_decay=weight_decay,
-                   grad_norm_sq_t=nsq, max_grad_norm=max_grad_norm)
+                   grad_norm_sq_t=nsq, max_grad_norm=max_grad_norm, grad_unscale=grad_unscale)
+    bump_weights_epoch()
     return nsq
+
+
+class FlatTrainer:
+    """The optimizer side of training/train.py:346-353,560-568 for one module (the UNet): all trainable parameters
+    and their gradients are re-homed as views of two flat fp32 buffers, so `backward()` accumulates straight into
+    the buffer the gradient all-reduce and the fused clip + AdamW kernel work on.
+
+        tr = FlatTrainer(unet, lr=3e-5)
+        loss, _ = e2e_ft_loss(unet, vae, scheduler, rgb, gt, mask, empty_encoding, "depth")
+        tr.backward(loss)            # (loss * LOSS_SCALE / accumulation_steps).backward()
+        tr.step()                    # all-reduce, clip, AdamW, zero the gradient buffer
+    """
+
+    def __init__(self, module, lr=3e-5, weight_decay=1e-2, max_grad_norm=1.0, accumulation_steps=1, group=None,
+                 loss_scale=LOSS_SCALE):
+        ps = [p for p in module.parameters() if p.requires_grad]
+        if not ps:
+            raise ValueError("no trainable parameters")
+        dev = ps[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in ps]                     # keep every view 16-byte aligned
+        total = sum(sizes)
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(ps, sizes):
+                if p.dtype != torch.float32:
+                    raise TypeError("FlatTrainer expects fp32 master parameters")
+                view = self.flat_param[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+                off += n
+        self.params, self.step_count = ps, 0
+        self.lr, self.weight_decay, self.max_grad_norm = lr, weight_decay, max_grad_norm
+        self.accumulation_steps, self.group, self.loss_scale = accumulation_steps, group, loss_scale
+
+    def backward(self, loss):
+        (loss * (self.loss_scale / self.accumulation_steps)).backward()
+
+    def step(self, lr=None):
+        self.step_count += 1
+        nsq = optimizer_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                              lr=self.lr if lr is None else lr, weight_decay=self.weight_decay,
+                              max_grad_norm=self.max_grad_norm, group=self.group, grad_unscale=1.0 / self.loss_scale)
+        self.flat_grad.zero_()
+        return nsq

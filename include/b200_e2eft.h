@@ -172,6 +172,10 @@ int b200_sumsq(const float* x, long long n, double* out, void* stream);
 int b200_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     const double* grad_norm_sq, float max_grad_norm, void* stream);
+/* Same with a loss-scaled gradient buffer: grad holds S*g and grad_norm_sq = |S*g|^2; grad_unscale = 1/S. */
+int b200_adamw_step_scaled(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                           const double* grad_norm_sq, float max_grad_norm, float grad_unscale, void* stream);
 
 /* ---- Backward pass (training/train.py:545-566, `accelerator.backward(loss)`).  The GEMM-shaped halves run on
  * b200_linear / b200_conv2d_nhwc with re-packed operands; these are the streaming / reduction kernels around them.

@@ -327,6 +327,24 @@ def decode_post_bwd(x, dout, normals=False):
     return xr.grad
 
 
+def grad_norm_sq(flat_grad):
+    return flat_grad.double().pow(2).sum().reshape(1)
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+               grad_norm_sq_t=None, max_grad_norm=0.0, grad_unscale=1.0):
+    clip = grad_unscale
+    if grad_norm_sq_t is not None and max_grad_norm > 0:
+        nrm = float(grad_norm_sq_t.sqrt()) * grad_unscale
+        clip = grad_unscale * min(1.0, max_grad_norm / (nrm + 1e-6))
+    g = grad * clip
+    param.mul_(1 - lr * weight_decay)
+    exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    param.addcdiv_(exp_avg, exp_avg_sq.sqrt() / math.sqrt(bc2) + eps, value=-lr / bc1)
+
+
 _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm_mean_rstd=group_norm_mean_rstd,
                  group_norm_bwd=group_norm_bwd, layer_norm=layer_norm, layer_norm_bwd=layer_norm_bwd,
                  attention_d64=attention_d64, softmax_rows=softmax_rows, softmax_bwd_rows=softmax_bwd_rows,
@@ -334,7 +352,7 @@ _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm
                  cast_f16=cast_f16, im2col3x3=im2col3x3, conv3x3_small_cout=conv3x3_small_cout,
                  timestep_embedding=timestep_embedding, nhwc_to_nchw_f32=nhwc_to_nchw_f32,
                  pointwise_nchw=pointwise_nchw, decode_post=decode_post, ssi_loss=ssi_loss, angular_loss=angular_loss,
-                 ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd)
+                 ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd, grad_norm_sq=grad_norm_sq, adamw_step=adamw_step)
 
 
 def install(monkeypatch):

@@ -256,3 +256,49 @@ def run_training_step_tiny(device="cuda:0", modality="depth"):
         den += gr.pow(2).sum().item()
     return dict(loss_engine=got.item(), loss_oracle=want.item(), loss_rel=abs(got.item() - want.item()) / abs(want.item()),
                 grad_global=(num / den) ** 0.5, grad_worst=worst, worst_name=worst_name, missing=missing)
+
+
+def run_training_loop_tiny(device="cuda:0", steps=3, lr=1e-4):
+    """training/train.py:469-568 for a few iterations (depth recipe, bs=2): e2e_ft_loss -> backward -> gradient clip
+    -> AdamW through FlatTrainer (flat buffers + fused CUDA optimizer) vs the oracle graph with
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.  Reports the per-step losses and the cosine similarity /
+    relative error of the accumulated parameter update."""
+    from diffusion_e2e_ft_b200.training import FlatTrainer, e2e_ft_loss
+    unet_ref, vae_ref = MG.build_tiny()
+    unet, vae = engine_from_oracle(unet_ref, vae_ref, device)
+    unet.requires_grad_(True)
+    unet_ref.requires_grad_(True)
+    vae_ref.requires_grad_(False)
+    start = {n: p.detach().clone() for n, p in unet_ref.named_parameters()}
+    opt = torch.optim.AdamW(unet_ref.parameters(), lr=lr, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    tr = FlatTrainer(unet, lr=lr, weight_decay=1e-2, max_grad_norm=1.0)
+    g = torch.Generator().manual_seed(21)
+    ctx = torch.randn(1, 77, 128, generator=g) * 0.5
+    sched_o, sched = OP.DDIMOneStep(), DDIMScheduler()
+    le, lo = [], []
+    for _ in range(steps):
+        rgb = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+        mask = torch.rand(2, 1, 64, 64, generator=g) > 0.2
+        gt = torch.rand(2, 1, 64, 64, generator=g) * 9.9 + 0.1
+        with torch.no_grad():
+            lat = OP.encode_rgb(vae_ref, rgb)
+        v = unet_ref(torch.cat([lat, torch.zeros_like(lat)], 1), 999, ctx.repeat(2, 1, 1)).sample
+        dec = OP.decode_latent(vae_ref, sched_o.pred_original_sample(v, 999, torch.zeros_like(lat)))
+        loss_o = OP.ssi_loss(dec.mean(1, keepdim=True).clamp(-1, 1), gt, mask)
+        opt.zero_grad()
+        loss_o.backward()
+        torch.nn.utils.clip_grad_norm_(unet_ref.parameters(), 1.0)
+        opt.step()
+        loss_e, _ = e2e_ft_loss(unet, vae, sched, rgb.to(device), gt.to(device), mask.to(device), ctx.to(device), "depth")
+        tr.backward(loss_e)
+        tr.step()
+        le.append(loss_e.item())
+        lo.append(loss_o.item())
+    dot = ne = no = 0.0
+    for n, p in unet.named_parameters():
+        de = p.detach().float().cpu() - start[n]
+        do = dict(unet_ref.named_parameters())[n].detach() - start[n]
+        dot += (de * do).sum().item()
+        ne += de.pow(2).sum().item()
+        no += do.pow(2).sum().item()
+    return dict(loss_engine=le, loss_oracle=lo, update_cosine=dot / (ne * no) ** 0.5, update_norm_ratio=(ne / no) ** 0.5)

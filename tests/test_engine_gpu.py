@@ -104,3 +104,16 @@ def test_training_micro_step_gradients_match_oracle(modality, tol):
     assert not r["missing"], r["missing"]
     assert r["loss_rel"] <= 3e-3, r
     assert r["grad_global"] <= tol and r["grad_worst"] <= 3 * tol, r
+
+
+def _check_loop(r):
+    for a, b in zip(r["loss_engine"], r["loss_oracle"]):
+        assert abs(a - b) / abs(b) <= 3e-3, r
+    assert r["update_cosine"] >= 0.98 and abs(r["update_norm_ratio"] - 1.0) <= 0.03, r
+
+
+@pytest.mark.gpu
+def test_training_loop_matches_oracle_adamw():
+    """Three iterations of training/train.py:469-568 (loss -> backward -> clip -> AdamW) on the engine (FlatTrainer:
+    flat buffers + fused CUDA clip/AdamW, loss-scaled fp16 backward) vs the oracle with torch.optim.AdamW."""
+    _check_loop(EC.run_training_loop_tiny())

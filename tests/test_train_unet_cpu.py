@@ -28,3 +28,58 @@ def test_training_micro_step_wiring(emulated, modality, tol):
     assert not r["missing"], r["missing"]
     assert r["loss_rel"] <= 3e-3, r
     assert r["grad_global"] <= tol and r["grad_worst"] <= 3 * tol, r
+
+
+def test_training_loop_wiring(emulated):
+    """flat parameter / gradient buffers, loss scaling, packed-weight cache invalidation after the optimizer step"""
+    from test_engine_gpu import _check_loop
+    _check_loop(EC.run_training_loop_tiny(device="cpu"))
+
+
+def test_two_rank_gloo_data_parallel_training_step():
+    """DDP semantics of training/train.py (accelerate): each rank runs the micro-step on its own images, the flat
+    gradient buffer is averaged over the ranks (one all-reduce), every rank applies the same clip + AdamW update.
+    world_size 2 on gloo with the kernels emulated: the ranks' parameters must stay identical, and differ from a
+    run without the exchange."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch, torch.distributed as dist
+torch.set_num_threads(4)
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests"); sys.path.insert(0, %r + "/tests/golden")
+import cpu_emulation, engine_checks as E, make_golden as MG
+from diffusion_e2e_ft_b200 import ops, DDIMScheduler
+from diffusion_e2e_ft_b200.training import FlatTrainer, e2e_ft_loss
+class MP:
+    def setattr(self, o, n, v): setattr(o, n, v)
+cpu_emulation.install(MP()); ops.FUSE_GN_STATS = False
+r = int(sys.argv[1])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29587", rank=r, world_size=2)
+unet_ref, vae_ref = MG.build_tiny()
+unet, vae = E.engine_from_oracle(unet_ref, vae_ref, "cpu")
+unet.requires_grad_(True)
+tr = FlatTrainer(unet, lr=1e-4)
+g = torch.Generator().manual_seed(100 + r)                     # different images on each rank
+rgb = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+gt = torch.rand(1, 1, 64, 64, generator=g) * 9.9 + 0.1
+mask = torch.rand(1, 1, 64, 64, generator=g) > 0.2
+ctx = MG.inputs(5, 1, 77, 128, scale=0.5)
+loss, _ = e2e_ft_loss(unet, vae, DDIMScheduler(), rgb, gt, mask, ctx, "depth")
+tr.backward(loss)
+local = tr.flat_grad.clone()
+tr.step()
+both = [torch.zeros_like(tr.flat_param) for _ in range(2)]
+dist.all_gather(both, tr.flat_param)
+assert torch.equal(both[0], both[1]), "ranks diverged"
+grads = [torch.zeros_like(local) for _ in range(2)]
+dist.all_gather(grads, local)
+assert not torch.allclose(grads[0], grads[1]), "ranks saw the same data"
+print("OK", float(loss))
+''' % (root, root, root)
+    ps = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+          for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in ps]
+    assert all(p.returncode == 0 for p in ps), outs
+    assert all(o[0].startswith("OK") for o in outs), outs
