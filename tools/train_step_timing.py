@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--breakdown", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "train_step.json"))
     a = ap.parse_args()
     from diffusion_e2e_ft_b200 import B200AutoencoderKL, B200UNet2DConditionModel, DDIMScheduler, ops
@@ -56,12 +57,28 @@ def main():
         losses.append(loss.item())
         if it >= a.warmup:
             times.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
+    # per-op-kind GPU time of one more iteration (CUDA events around every op: adds launch gaps, so the sums
+    # are kernel time, not wall time)
+    breakdown = {}
+    if a.breakdown:
+        ops.STATS.time_all, ops.STATS.op_events = True, []
+        loss, _ = e2e_ft_loss(unet, vae, sched, rgb, gt, mask, ete, "depth")
+        n_fwd = len(ops.STATS.op_events)
+        tr.backward(loss)
+        tr.step()
+        torch.cuda.synchronize()
+        ops.STATS.time_all = False
+        for i, (name, e0, e1) in enumerate(ops.STATS.op_events):
+            k = ("fwd." if i < n_fwd else "bwd.") + name
+            breakdown[k] = breakdown.get(k, 0.0) + e0.elapsed_time(e1)
+        breakdown = {k: round(v, 2) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])}
     fwd = sum(t[0] for t in times) / len(times)
     bwd = sum(t[1] for t in times) / len(times)
     res = dict(what="fine-tuning iteration, full SD-2 UNet + VAE, depth recipe", batch=a.batch, height=a.height,
                width=a.width, steps=a.steps, warmup=a.warmup, forward_ms=fwd, backward_optimizer_ms=bwd,
                ms_per_step=fwd + bwd, images_per_s=a.batch / ((fwd + bwd) / 1e3), losses=losses,
                launches_last_step=ops.STATS.launches, peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30,
+               breakdown_ms=breakdown, breakdown_sum_ms=round(sum(breakdown.values()), 1),
                finite=all(l == l and abs(l) < 1e9 for l in losses), time=time.strftime("%Y-%m-%d %H:%M:%S"))
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
