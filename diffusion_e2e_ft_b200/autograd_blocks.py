@@ -211,17 +211,48 @@ class _UpsampleFn(torch.autograd.Function):
         if _any(ctx, 3):
             dwp, gb = bw.conv_wgrad(x16, d16, TAPS3, up=2)
             gw = bw.unpack_conv_grad(dwp, C)
-        pb = _bwd_cache(m).get([m.conv.weight], lambda: pack_upsample_conv_dgrad(m._pack_phases()))
-        dx = bw.conv_dgrad(d16, None, C, "up", out_dtype=F32, packed=pb)
+        pb = _bwd_cache(m).get([m.conv.weight], lambda: dict(up=pack_upsample_conv_dgrad(m._pack_phases())))
+        if "up" not in pb:
+            pb["up"] = pack_upsample_conv_dgrad(m._pack_phases())
+        dx = bw.conv_dgrad(d16, None, C, "up", out_dtype=F32, packed=pb["up"])
         return None, None, dx, gw, gb
+
+
+class _UpsampleSizeFn(torch.autograd.Function):
+    """nearest upsample to an explicit size (unet_2d_condition.py:1185-1186, latent sizes not divisible by
+    2^levels) + conv3x3: Upsample2D.run's second branch."""
+
+    @staticmethod
+    def forward(ctx, m, out_hw, box, x, weight, bias):
+        pk = m._pk2.get(list(m.parameters()), lambda: dict(w=ops.pack_conv(m.conv.weight), b=_f32(m.conv.bias)))
+        C = x.shape[3]
+        up = ops.upsample_nearest(x, out_hw)
+        out = ops.conv2d(up, pk["w"], C, bias=pk["b"], out_dtype=F32, stats=True)
+        ctx.m, ctx.saved, ctx.in_hw = m, (up,), tuple(x.shape[1:3])
+        return _stash(out, box)
+
+    @staticmethod
+    def backward(ctx, dout):
+        m = ctx.m
+        (up,) = ctx.saved
+        C = up.shape[3]
+        d16 = ops.cast_f16(dout.contiguous())
+        gw = gb = None
+        if _any(ctx, 4):
+            dwp, gb = bw.conv_wgrad(up, d16, TAPS3)
+            gw = bw.unpack_conv_grad(dwp, C)
+        pb = _bwd_cache(m).get([m.conv.weight], lambda: dict(s1=pack_conv_dgrad_s1(m.conv.weight)))
+        if "s1" not in pb:
+            pb["s1"] = pack_conv_dgrad_s1(m.conv.weight)
+        dup = bw.conv_dgrad(d16, None, C, "s1", out_dtype=F32, packed=pb["s1"])
+        return None, None, None, ops.upsample_nearest_bwd(dup, ctx.in_hw), gw, gb
 
 
 def upsample(m, x, out_hw=None):
     NB, H, W, C = x.shape
-    if out_hw is not None and tuple(out_hw) != (2 * H, 2 * W):
-        raise NotImplementedError("training through the explicit-size upsample (latent sizes not divisible by 8) "
-                                  "is not implemented yet")
     box = {}
+    if out_hw is not None and tuple(out_hw) != (2 * H, 2 * W):
+        return _attach(_UpsampleSizeFn.apply(m, tuple(out_hw), box, x, m.conv.weight, m.conv.bias), box)
     return _attach(_UpsampleFn.apply(m, box, x, m.conv.weight, m.conv.bias), box)
 
 

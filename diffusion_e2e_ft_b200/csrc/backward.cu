@@ -550,6 +550,30 @@ __global__ void decode_post_bwd_kernel(const float* __restrict__ x, const float*
   }
 }
 
+// ------------------------------------------------------------------------------------ nearest-upsample backward
+// dx[n,h,w,:] (+ add) = sum of dy[n,oh,ow,:] over the output pixels whose torch-nearest source
+// (floor(o * in / out), the map of upsample_nearest_kernel) is (h, w).  fp32 NHWC, C % 4 == 0.
+__global__ void upsample_nearest_bwd_kernel(const float* __restrict__ dy, int NB, int H, int W, int C, int OH, int OW,
+                                            const float* add, float* dx) {
+  const int V = C / 4;
+  const long long total = (long long)NB * H * W * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    const long long pix = i / V;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    const int oh0 = (int)(((long long)h * OH + H - 1) / H), ow0 = (int)(((long long)w * OW + W - 1) / W);
+    float4 acc = add ? reinterpret_cast<const float4*>(add + pix * C)[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oh = oh0; oh < OH && (int)(((long long)oh * H) / OH) == h; ++oh)
+      for (int ow = ow0; ow < OW && (int)(((long long)ow * W) / OW) == w; ++ow) {
+        const float4 d = reinterpret_cast<const float4*>(dy + (((long long)n * OH + oh) * OW + ow) * C)[v];
+        acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+      }
+    reinterpret_cast<float4*>(dx + pix * C)[v] = acc;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -774,5 +798,15 @@ extern "C" int b200_decode_post_bwd(const float* x, const float* dout, int NB, l
   B200_CHECK_ARG(x && dout && dx && NB > 0 && HW > 0 && (mode == 2 || mode == 3), "b200_decode_post_bwd: bad arguments");
   decode_post_bwd_kernel<<<bw_loss_grid(HW, NB), 256, 0, (cudaStream_t)stream>>>(x, dout, HW, mode, dx);
   B200_CHECK_LAUNCH("decode_post_bwd_kernel");
+  return 0;
+}
+
+extern "C" int b200_upsample_nearest_bwd(const float* dy, int NB, int H, int W, int C, int OH, int OW, const float* add,
+                                         float* dx, void* stream) {
+  B200_CHECK_ARG(dy && dx && NB > 0 && H > 0 && W > 0 && OH >= H && OW >= W, "b200_upsample_nearest_bwd: bad arguments");
+  B200_CHECK_ARG(C % 4 == 0, "b200_upsample_nearest_bwd: C=%d must be a multiple of 4", C);
+  const long long total = (long long)NB * H * W * (C / 4);
+  upsample_nearest_bwd_kernel<<<bw_grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, NB, H, W, C, OH, OW, add, dx);
+  B200_CHECK_LAUNCH("upsample_nearest_bwd_kernel");
   return 0;
 }

@@ -661,3 +661,18 @@ def decode_post_bwd(x, dout, normals=False):
     _ck(_lib.load().b200_decode_post_bwd(_p(x), _p(dout), NB, H * W, 3 if normals else 2, _p(dx), _stream()),
         "b200_decode_post_bwd")
     return dx
+
+
+@_timed("bwd_misc")
+def upsample_nearest_bwd(dy, in_hw, add=None):
+    """dy: fp32 [NB,OH,OW,C] -> fp32 [NB,H,W,C] (+ add): backward of upsample_nearest."""
+    _need_cuda(dy, add)
+    assert dy.dtype == F32 and dy.is_contiguous()
+    NB, OH, OW, C = dy.shape
+    H, W = in_hw
+    dx = torch.empty((NB, H, W, C), dtype=F32, device=dy.device)
+    if add is not None:
+        assert add.dtype == F32 and add.is_contiguous() and add.shape == dx.shape
+    _ck(_lib.load().b200_upsample_nearest_bwd(_p(dy), NB, H, W, C, OH, OW, _p(add), _p(dx), _stream()),
+        "b200_upsample_nearest_bwd")
+    return dx

@@ -264,8 +264,7 @@ class B200UNet2DConditionModel(nn.Module):
         B, _, H, W = sample.shape
         dev = sample.device
         n_up = len(cfg["block_out_channels"]) - 1
-        if (H % (2 ** n_up) != 0) or (W % (2 ** n_up) != 0):
-            raise NotImplementedError("training needs latent sizes divisible by %d for now" % (2 ** n_up))
+        forward_size = (H % (2 ** n_up) != 0) or (W % (2 ** n_up) != 0)      # unet_2d_condition.py:920-930
         if not torch.is_tensor(timestep):
             t = torch.full((B,), float(timestep), dtype=F32, device=dev)
         else:
@@ -299,12 +298,12 @@ class B200UNet2DConditionModel(nn.Module):
         for blk in self.up_blocks:
             for i, r in enumerate(blk.resnets):
                 skip = skips.pop()
-                last = (i == len(blk.resnets) - 1) and blk.upsamplers is not None
+                last = (i == len(blk.resnets) - 1) and blk.upsamplers is not None and not forward_size
                 x = ab.resnet(r, x, temb_of[id(r)], skip, f16_copy=last and blk.attentions is None)
                 if blk.attentions is not None:
                     x = ab.transformer(blk.attentions[i], x, ctx16, f16_copy=last)
             if blk.upsamplers is not None:
-                x = ab.upsample(blk.upsamplers[0], x)
+                x = ab.upsample(blk.upsamplers[0], x, tuple(skips[-1].shape[1:3]) if forward_size else None)
         if not hasattr(self, "_conv_out_run") or self._conv_out_run.conv is not self.conv_out:
             self._conv_out_run = ConvOutSmall(self.conv_norm_out, self.conv_out)
         out = ab.conv_out(self._conv_out_run, x)

@@ -222,6 +222,10 @@ int b200_ssi_loss_bwd(const float* pred, const float* target, const unsigned cha
 int b200_angular_loss_bwd(const float* pred, const float* target, const unsigned char* mask, int B, long long HW,
                           double* workspace, const float* grad_out, float* dpred, void* stream);
 int b200_decode_post_bwd(const float* x, const float* dout, int NB, long long HW, int mode, float* dx, void* stream);
+/* Backward of b200_upsample_nearest_nhwc (explicit output size, unet_2d_condition.py:1185-1186): fp32 NHWC,
+ * dx[n,h,w,:] = (add) + sum of dy over the output pixels whose nearest source is (h,w). */
+int b200_upsample_nearest_bwd(const float* dy, int NB, int H, int W, int C, int OH, int OW, const float* add,
+                              float* dx, void* stream);
 
 /* fp32 <-> fp16 casts / layout helpers used at module boundaries. */
 int b200_cast_f32_to_f16(const float* x, void* y, long long n, void* stream);

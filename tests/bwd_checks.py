@@ -268,7 +268,23 @@ def check_decode_post_bwd(normals, B=2, H=24, W=40, seed=45):
     return rel_l2(got, xr.grad) + fwd, 1e-5
 
 
+def check_upsample_nearest_bwd(NB=2, H=8, W=10, OH=15, OW=20, C=64, add=True, seed=47):
+    dy = _rand(NB, OH, OW, C, seed=seed, dtype=F32)
+    addt = _rand(NB, H, W, C, seed=seed + 1, dtype=F32) if add else None
+    got = ops.upsample_nearest_bwd(dy, (H, W), addt)
+    x = _rand(NB, H, W, C, seed=seed + 2)
+    up = ops.upsample_nearest(x, (OH, OW))
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref_up = F.interpolate(xr, size=(OH, OW), mode="nearest")
+    (ref_up * dy.permute(0, 3, 1, 2)).sum().backward()
+    fwd = (up.float() - ref_up.detach().permute(0, 2, 3, 1)).abs().max().item()
+    return rel_l2(got, xr.grad.permute(0, 2, 3, 1) + (addt if add else 0)) + fwd, 1e-6
+
+
 BWD_CHECKS = {
+    "bwd_upsample_nearest_8x10_to_15x20": check_upsample_nearest_bwd,
+    "bwd_upsample_nearest_6x19_to_11x38": lambda: check_upsample_nearest_bwd(1, 6, 19, 11, 38, 128, False),
     "bwd_ssi_loss": check_ssi_loss_bwd,
     "bwd_angular_loss": check_angular_loss_bwd,
     "bwd_decode_post_depth": lambda: check_decode_post_bwd(False),

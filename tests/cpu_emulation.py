@@ -345,6 +345,26 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr=3e-5, betas=(0.9, 0.99
     param.addcdiv_(exp_avg, exp_avg_sq.sqrt() / math.sqrt(bc2) + eps, value=-lr / bc1)
 
 
+def _nearest_index(n_in, n_out):
+    return torch.clamp((torch.arange(n_out) * n_in) // n_out, max=n_in - 1)
+
+
+def upsample_nearest(x, out_hw):
+    OH, OW = out_hw
+    ih, iw = _nearest_index(x.shape[1], OH), _nearest_index(x.shape[2], OW)
+    return x[:, ih][:, :, iw].half().contiguous()
+
+
+def upsample_nearest_bwd(dy, in_hw, add=None):
+    H, W = in_hw
+    NB, OH, OW, C = dy.shape
+    ih, iw = _nearest_index(H, OH), _nearest_index(W, OW)
+    dx = torch.zeros(NB, H, W, C)
+    tmp = torch.zeros(NB, H, OW, C).index_add_(1, ih, dy.float())
+    dx.index_add_(2, iw, tmp)
+    return dx if add is None else dx + add
+
+
 _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm_mean_rstd=group_norm_mean_rstd,
                  group_norm_bwd=group_norm_bwd, layer_norm=layer_norm, layer_norm_bwd=layer_norm_bwd,
                  attention_d64=attention_d64, softmax_rows=softmax_rows, softmax_bwd_rows=softmax_bwd_rows,
@@ -352,7 +372,8 @@ _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm
                  cast_f16=cast_f16, im2col3x3=im2col3x3, conv3x3_small_cout=conv3x3_small_cout,
                  timestep_embedding=timestep_embedding, nhwc_to_nchw_f32=nhwc_to_nchw_f32,
                  pointwise_nchw=pointwise_nchw, decode_post=decode_post, ssi_loss=ssi_loss, angular_loss=angular_loss,
-                 ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd, grad_norm_sq=grad_norm_sq, adamw_step=adamw_step)
+                 ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd, grad_norm_sq=grad_norm_sq, adamw_step=adamw_step,
+                 upsample_nearest=upsample_nearest, upsample_nearest_bwd=upsample_nearest_bwd)
 
 
 def install(monkeypatch):

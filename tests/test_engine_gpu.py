@@ -117,3 +117,13 @@ def test_training_loop_matches_oracle_adamw():
     """Three iterations of training/train.py:469-568 (loss -> backward -> clip -> AdamW) on the engine (FlatTrainer:
     flat buffers + fused CUDA clip/AdamW, loss-scaled fp16 backward) vs the oracle with torch.optim.AdamW."""
     _check_loop(EC.run_training_loop_tiny())
+
+
+@pytest.mark.gpu
+def test_unet_backward_odd_latent_size():
+    """15x20 latents (480x640 images / 4, the Hypersim recipe's aspect): odd levels -> stride-2 dgrad with a cropped
+    border, explicit-size nearest upsample and its backward, attention lengths that are not multiples of 8."""
+    r = EC.run_unet_backward_tiny(hw=(15, 20))
+    assert not r["missing"], r["missing"]
+    assert r["forward"] <= 3e-3, r
+    assert r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2, r

@@ -14,8 +14,9 @@ def emulated(monkeypatch):
     monkeypatch.setattr(ops, "FUSE_GN_STATS", False)
 
 
-def test_unet_backward_wiring_matches_oracle_autograd(emulated):
-    r = EC.run_unet_backward_tiny(device="cpu")
+@pytest.mark.parametrize("hw", [(16, 16), (15, 20), (11, 38)])
+def test_unet_backward_wiring_matches_oracle_autograd(emulated, hw):
+    r = EC.run_unet_backward_tiny(device="cpu", hw=hw)
     assert not r["missing"], r["missing"]
     assert r["n_params"] == 686
     assert r["forward"] <= 3e-3, r
