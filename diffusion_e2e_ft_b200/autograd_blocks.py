@@ -270,13 +270,11 @@ def _transformer_params(m):
 
 
 class _TransformerFn(torch.autograd.Function):
-    """Transformer2DModel.run (one BasicTransformerBlock, non-joint) + its backward."""
+    """Transformer2DModel.run (one BasicTransformerBlock; plain or GeoWizard joint self-attention) + its backward."""
 
     @staticmethod
     def forward(ctx, m, f16_copy, box, x, ctx16, *params):
         blk = m.transformer_blocks[0]
-        if blk.joint:
-            raise NotImplementedError("training through the joint (GeoWizard) attention is not implemented yet")
         own = [m.norm.weight, m.norm.bias, m.proj_in.weight, m.proj_in.bias, m.proj_out.weight, m.proj_out.bias]
         pk = m._pk.get(own, lambda: dict(g=_f32(m.norm.weight), b=_f32(m.norm.bias),
                                          wi=_f16(m.proj_in.weight), bi=_f32(m.proj_in.bias),
@@ -289,7 +287,8 @@ class _TransformerFn(torch.autograd.Function):
         h0 = ops.linear(hn.view(B * L, C), pk["wi"], pk["bi"], out_dtype=F32)
         n1 = ops.layer_norm(h0, *bp["ln"][0])
         qkv = ops.linear(n1, bp["wqkv"]).view(B, L, 3 * C)
-        o = ops.attention_d64(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, scale)
+        o = ops.attention_d64(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, scale,
+                              kv_segments=2 if blk.joint else 1)
         h1 = ops.linear(o.view(B * L, C), bp["wo1"], bp["bo1"], residual=h0, out_dtype=F32)
         n2 = ops.layer_norm(h1, *bp["ln"][1])
         q2 = ops.linear(n2, bp["wq2"]).view(B, L, C)
@@ -353,8 +352,23 @@ class _TransformerFn(torch.autograd.Function):
         # ---- self attention: h1 = h0 + W_o1 attn(q, k, v) + b_o1
         do1, g["wo1"], g["bo1"] = bw.linear_bwd(o.view(B * L, C), bp["wo1"], ops.cast_f16(dh1), need_dw=train)
         dqkv = torch.empty((B, L, 3 * C), dtype=F16, device=dev)
-        bw.attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], do1.view(B, L, C), heads, scale,
-                         outs=(dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:]))
+        if not blk.joint:
+            bw.attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], do1.view(B, L, C), heads, scale,
+                             outs=(dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:]))
+        else:
+            # XFormersJointAttnProcessor (attention.py:430-513): images i and i + B/2 (the depth / normal halves) both
+            # attend to the concatenation of their two key/value sets.  Their queries therefore form ONE attention
+            # problem with 2L queries over 2L keys, whose dK/dV rows are exactly the two images' own gradients.
+            half = B // 2
+            do1 = do1.view(B, L, C)
+            for i in range(half):
+                pair = torch.cat([qkv[i], qkv[i + half]], dim=0).unsqueeze(0)          # [1, 2L, 3C] (host re-layout)
+                dop = torch.cat([do1[i], do1[i + half]], dim=0).unsqueeze(0)
+                dpair = torch.empty((1, 2 * L, 3 * C), dtype=F16, device=dev)
+                bw.attention_bwd(pair[..., :C], pair[..., C:2 * C], pair[..., 2 * C:], dop, heads, scale,
+                                 outs=(dpair[..., :C], dpair[..., C:2 * C], dpair[..., 2 * C:]))
+                dqkv[i].copy_(dpair[0, :L])
+                dqkv[i + half].copy_(dpair[0, L:])
         dn1, dwqkv, _ = bw.linear_bwd(n1, bp["wqkv"], dqkv.view(B * L, 3 * C), need_dw=train, bias=False)
         if train:
             g["wq1"], g["wk1"], g["wv1"] = dwqkv[:C], dwqkv[C:2 * C], dwqkv[2 * C:]

@@ -179,20 +179,26 @@ def run_training_forward_tiny(device="cuda:0", modality="depth"):
     return dict(loss_engine=got.item(), loss_oracle=want.item(), rel_err=abs(got.item() - want.item()) / abs(want.item()))
 
 
-def run_unet_backward_tiny(device="cuda:0", hw=(16, 16), ctx_tokens=77):
+def run_unet_backward_tiny(device="cuda:0", hw=(16, 16), ctx_tokens=77, kind="marigold"):
     """Row a10: gradients of every UNet parameter through the engine's autograd blocks vs torch.autograd through
     the fp32 oracle, same weights / inputs / upstream gradient (bs=2).  Returns the forward error, the global
     relative L2 error over all parameter gradients and the worst single parameter."""
-    unet_ref, _ = MG.build_tiny()
+    unet_ref, _ = MG.build_tiny(kind)
     unet, _ = engine_from_oracle(unet_ref, None, device)
     unet.requires_grad_(True)
     unet_ref.requires_grad_(True)
     x = MG.inputs(1, 2, 8, *hw)
-    c = MG.inputs(2, 2, ctx_tokens, 128, scale=0.5)
     dy = MG.inputs(7, 2, 4, *hw)
-    y = unet(x.to(device), 999, c.to(device)).sample
+    kw_e, kw_r = {}, {}
+    if kind == "geowizard":           # depth / normal halves, 1 image-embedding token, domain class embedding
+        c = MG.inputs(2, 2, 1, 96, scale=0.5)
+        cl = MG.inputs(3, 2, 10, scale=0.5)
+        kw_e, kw_r = dict(class_labels=cl.to(device)), dict(class_labels=cl)
+    else:
+        c = MG.inputs(2, 2, ctx_tokens, 128, scale=0.5)
+    y = unet(x.to(device), 999, c.to(device), **kw_e).sample
     (y * dy.to(device)).sum().backward()
-    yr = unet_ref(x, 999, c).sample
+    yr = unet_ref(x, 999, c, **kw_r).sample
     (yr * dy).sum().backward()
     ref = dict(unet_ref.named_parameters())
     num = den = 0.0

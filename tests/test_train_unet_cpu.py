@@ -84,3 +84,12 @@ print("OK", float(loss))
     outs = [p.communicate(timeout=600) for p in ps]
     assert all(p.returncode == 0 for p in ps), outs
     assert all(o[0].startswith("OK") for o in outs), outs
+
+
+def test_geowizard_joint_attention_backward_wiring(emulated):
+    """GeoWizard-shaped UNet (class-embedding projection, 1 context token, joint self-attention over the depth /
+    normal pair): the pair is differentiated as one 2L x 2L attention problem."""
+    r = EC.run_unet_backward_tiny(device="cpu", kind="geowizard")
+    assert not r["missing"], r["missing"]
+    assert r["forward"] <= 3e-3, r
+    assert r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2, r
