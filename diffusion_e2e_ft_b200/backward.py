@@ -37,17 +37,90 @@ def linear_bwd(a, w, dy, need_da=True, da_dtype=F16, da_add=None, need_dw=True, 
 
 
 # -------------------------------------------------------------------------------------------------- conv
+# Experimental (round-2 work, OFF by default; host algebra verified on CPU with the kernels emulated, first hardware
+# run pending — tools/pending_gpu_checks.py):
+#   WGRAD_PADDED  stride-1 3x3 convs: one zero-padded planar copy of X and three column-shifted copies of dY instead
+#                 of nine shifted copies of X; a kernel row (ky) is a 16-byte-aligned pointer offset of ky*Wp into X.
+#   WGRAD_SPLIT_K split the pixel contraction over `batch` so a Cout x Cin weight-gradient GEMM fills the 148 SMs;
+#                 value = target number of CTAs (0 = no split); partial sums are reduced by `col_sum`.
+WGRAD_PADDED = False
+WGRAD_SPLIT_K = 0
+WGRAD_MIN_KBLOCKS = 8        # at least this many 64-wide k-blocks per split
+
+
+def _split_plan(K, cout, cin):
+    """(S, Kc): number of K chunks and chunk length (multiple of 64) for a [cout x cin] GEMM over K."""
+    kb = (K + 63) // 64
+    if WGRAD_SPLIT_K <= 0:
+        return 1, kb * 64
+    tiles = ((cout + 127) // 128) * ((cin + 159) // 160)
+    S = max(1, min(WGRAD_SPLIT_K // max(tiles, 1), kb // WGRAD_MIN_KBLOCKS))
+    kc = (kb + S - 1) // S
+    return (kb + kc - 1) // kc, kc * 64
+
+
+def _wgrad_taps(x, dy, taps, stride, up):
+    """Validated path: one K-major copy of dY, one shifted K-major copy of X per tap, one GEMM per tap."""
+    NB, Ho, Wo, Cout = dy.shape
+    Cin = x.shape[3]
+    P = NB * Ho * Wo
+    S, Kc = _split_plan(P, Cout, Cin)
+    if S == 1:
+        dyt = ops.gather_planar(dy)                                          # [Cout, P8]
+        dwp = torch.empty((Cout, len(taps) * Cin), dtype=F32, device=x.device)
+        for t, (ty, tx) in enumerate(taps):
+            xt = ops.gather_planar(x, out_hw=(Ho, Wo), stride=stride, up=up, off=(ty, tx))   # [Cin, P8]
+            ops.linear(dyt, xt, out=dwp[:, t * Cin:(t + 1) * Cin], out_dtype=F32)
+        return dwp
+    ld = S * Kc
+    dyt = ops.gather_planar(dy, out=torch.empty((Cout, ld), dtype=F16, device=x.device))
+    part = torch.empty((S, Cout, len(taps) * Cin), dtype=F32, device=x.device)
+    xt = torch.empty((Cin, ld), dtype=F16, device=x.device)
+    a3 = dyt.as_strided((S, Cout, Kc), (Kc, ld, 1))
+    w3 = xt.as_strided((S, Cin, Kc), (Kc, ld, 1))
+    for t, (ty, tx) in enumerate(taps):
+        ops.gather_planar(x, out_hw=(Ho, Wo), stride=stride, up=up, off=(ty, tx), out=xt)
+        ops.linear(a3, w3, out=part[:, :, t * Cin:(t + 1) * Cin], out_dtype=F32)
+    return ops.col_sum(part.view(S, -1)).view(Cout, len(taps) * Cin)
+
+
+def _wgrad_padded(x, dy):
+    """3x3 / stride 1 / pad 1.  Planar geometry (Hp, Wp) = (H + 2, ru8(W + 2)), flat index f = (n*Hp + i)*Wp + j:
+         Xp[ci][f]     = X[n, i-1, j-1, ci]                 (zero border)
+         dYk[kx][co][f] = dY[n, i, j-kx, co]                (rows i >= H and columns outside the image zero)
+       => dW[co][ky][kx][ci] = sum_f dYk[kx][co][f] * Xp[ci][f + ky*Wp]."""
+    NB, H, W, Cout = dy.shape
+    Cin = x.shape[3]
+    Hp, Wp = H + 2, ops._ru8(W + 2)
+    K = NB * Hp * Wp
+    S, Kc = _split_plan(K, Cout, Cin)
+    ld = S * Kc                                                              # >= K, multiple of 64, zero tail
+    dev = x.device
+    xp = torch.zeros((Cin + 1, ld), dtype=F16, device=dev)                   # +1 row: reads at f + 2*Wp stay inside
+    ops.gather_planar(x, out_hw=(Hp, Wp), off=(-1, -1), out=xp[:Cin])
+    part = torch.empty((S, Cout, 9 * Cin), dtype=F32, device=dev)
+    dyk = torch.empty((Cout, ld), dtype=F16, device=dev)
+    a3 = dyk.as_strided((S, Cout, Kc), (Kc, ld, 1))
+    for kx in range(3):
+        ops.gather_planar(dy, out_hw=(Hp, Wp), off=(0, -kx), out=dyk)
+        for ky in range(3):
+            w3 = xp.as_strided((S, Cin, Kc), (Kc, ld, 1), ky * Wp)
+            t = ky * 3 + kx
+            ops.linear(a3, w3, out=part[:, :, t * Cin:(t + 1) * Cin], out_dtype=F32)
+    if S == 1:
+        return part[0]
+    return ops.col_sum(part.view(S, -1)).view(Cout, 9 * Cin)
+
+
 def conv_wgrad(x, dy, taps=TAPS3, stride=1, up=1, bias=True):
     """Weight gradient of out[n,o,p,:] = sum_t Wp[:, t*Cin:(t+1)*Cin] @ x_up[n, stride*o+ty, stride*p+tx, :]
     (x_up = nearest-`up`x of x).  x [NB,H,W,Cin], dy [NB,Ho,Wo,Cout] fp16 NHWC.
     Returns (dWp fp32 [Cout, T*Cin] in the packed forward layout, db fp32 [Cout] | None)."""
-    NB, Ho, Wo, Cout = dy.shape
-    Cin = x.shape[3]
-    dyt = ops.gather_planar(dy)                                          # [Cout, P8]
-    dwp = torch.empty((Cout, len(taps) * Cin), dtype=F32, device=x.device)
-    for t, (ty, tx) in enumerate(taps):
-        xt = ops.gather_planar(x, out_hw=(Ho, Wo), stride=stride, up=up, off=(ty, tx))   # [Cin, P8]
-        ops.linear(dyt, xt, out=dwp[:, t * Cin:(t + 1) * Cin], out_dtype=F32)
+    Cout = dy.shape[3]
+    if WGRAD_PADDED and stride == 1 and up == 1 and list(taps) == list(TAPS3) and x.shape[:3] == dy.shape[:3]:
+        dwp = _wgrad_padded(x, dy)
+    else:
+        dwp = _wgrad_taps(x, dy, taps, stride, up)
     db = ops.col_sum(dy.reshape(-1, Cout)) if bias else None
     return dwp, db
 

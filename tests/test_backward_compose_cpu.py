@@ -28,3 +28,17 @@ COMPOSED = ["bwd_linear", "bwd_conv_wgrad_s1", "bwd_conv_wgrad_s2", "bwd_conv_wg
 def test_backward_composition(emulated, name):
     err, tol = bwd_checks.BWD_CHECKS[name]()
     assert err <= max(tol, 3e-3), f"{name}: {err:.3e}"
+
+
+@pytest.mark.parametrize("padded,split", [(True, 0), (False, 64), (True, 64)])
+@pytest.mark.parametrize("name", ["bwd_conv_wgrad_s1", "bwd_conv_wgrad_s2", "bwd_conv_wgrad_up"])
+def test_experimental_wgrad_modes(emulated, monkeypatch, name, padded, split):
+    """round-2 weight-gradient variants (padded planar operands, split-K over the batch dimension): same result"""
+    from diffusion_e2e_ft_b200 import backward as bw
+    monkeypatch.setattr(bw, "WGRAD_PADDED", padded)
+    monkeypatch.setattr(bw, "WGRAD_SPLIT_K", split)
+    monkeypatch.setattr(bw, "WGRAD_MIN_KBLOCKS", 1)
+    if split:
+        assert bw._split_plan(240, 128, 64)[0] > 1
+    err, tol = bwd_checks.BWD_CHECKS[name]()
+    assert err <= 3e-3, f"{name}: {err:.3e}"
