@@ -11,8 +11,6 @@ names, so reference checkpoints load unchanged.  Packed fp1
 derived lazily from the fp32 master parameters and re-derived whenever a parameter changes
 (`_version` / storage pointer), so optimizers and `load_state_dict` just work.
 """
-import math
-
 import torch
 import torch.nn as nn
 

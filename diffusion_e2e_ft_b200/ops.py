@@ -1,9 +1,10 @@
 """Torch-tensor wrappers over the C ABI (PyTorch tensors in, PyTorch tensors out).
 
 PyTorch only owns memory and streams here: every arithmetic op is a kernel of libb200_e2eft.so
-launched on `torch.cuda.current_stream()`.  Nothing in this module computes with torch ops.
+launched on `torch.cuda.current_stream()`.  Nothing in this module computes with torch ops, with two marked
+exceptions that are O(channels) in size: dtype conversions of masks / loss inputs at the API boundary and the
+final [NB, C, 2] -> [C, 2] fold of the GroupNorm-backward partial sums.
 """
-import ctypes
 from ctypes import c_int, c_void_p
 
 import torch

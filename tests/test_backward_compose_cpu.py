@@ -3,14 +3,9 @@ transposes, tap lists, head views, padding — with every CUDA kernel replaced b
 documented contract (include/b200_e2eft.h).  The kernels themselves are checked on the GPU (`bwd_*` checks);
 this file only makes sure the compositions ask them for the right thing.  Test infrastructure only."""
 import pytest
-import torch
-import torch.nn.functional as F
 
 import bwd_checks
 import cpu_emulation
-from diffusion_e2e_ft_b200 import ops
-
-F16, F32 = torch.float16, torch.float32
 
 
 @pytest.fixture
