@@ -60,7 +60,7 @@ class _ResnetFn(torch.autograd.Function):
     """ResnetBlock2D.run + its backward.  inputs: x [NB,H,W,C1] fp32, skip [NB,H,W,C2] | None, temb [NB,cout] | None."""
 
     @staticmethod
-    def forward(ctx, m, f16_copy, box, x, skip, temb, *params):
+    def run(m, f16_copy, x, skip, temb):
         pk = m._packed()
         xs = [x] if skip is None else [x, skip]
         mr1 = ops.group_norm_mean_rstd(x, m.eps, m.groups, skip)
@@ -78,14 +78,21 @@ class _ResnetFn(torch.autograd.Function):
         else:
             out = ops.conv2d(a2, pk["w2"], m.cout, bias=pk["c2b"], residual=x, out_dtype=F32, stats=True,
                              f16_copy=f16_copy)
+        return out, (xs, mr1, a1, raw, h, mr2, a2)
+
+    @staticmethod
+    def forward(ctx, m, f16_copy, box, x, skip, temb, *params):
+        out, saved = _ResnetFn.run(m, f16_copy, x, skip, temb)
         ctx.m, ctx.has_temb = m, temb is not None
-        ctx.saved = (xs, mr1, a1, raw, h, mr2, a2)
+        # gradient checkpointing (unet.enable_gradient_checkpointing, train.py:358-359): keep the block inputs only
+        # and re-run the block's forward kernels at the start of its backward
+        ctx.saved, ctx.inputs = (None, (f16_copy, x, skip, temb)) if box.get("ckpt") else (saved, None)
         return _stash(out, box)
 
     @staticmethod
     def backward(ctx, dout):
         m = ctx.m
-        xs, mr1, a1, raw, h, mr2, a2 = ctx.saved
+        xs, mr1, a1, raw, h, mr2, a2 = ctx.saved if ctx.saved is not None else _ResnetFn.run(m, *ctx.inputs)[1]
         pk = m._packed()
         train = _any(ctx, 6)
         short = m.conv_shortcut is not None
@@ -143,8 +150,8 @@ class _ResnetFn(torch.autograd.Function):
                 dtemb if ctx.has_temb else None, *grads)
 
 
-def resnet(m, x, temb=None, skip=None, f16_copy=False):
-    box = {}
+def resnet(m, x, temb=None, skip=None, f16_copy=False, ckpt=False):
+    box = {"ckpt": ckpt}
     return _attach(_ResnetFn.apply(m, f16_copy, box, x, skip, temb, *_resnet_params(m)), box)
 
 
@@ -273,7 +280,7 @@ class _TransformerFn(torch.autograd.Function):
     """Transformer2DModel.run (one BasicTransformerBlock; plain or GeoWizard joint self-attention) + its backward."""
 
     @staticmethod
-    def forward(ctx, m, f16_copy, box, x, ctx16, *params):
+    def run(m, f16_copy, x, ctx16):
         blk = m.transformer_blocks[0]
         own = [m.norm.weight, m.norm.bias, m.proj_in.weight, m.proj_in.bias, m.proj_out.weight, m.proj_out.bias]
         pk = m._pk.get(own, lambda: dict(g=_f32(m.norm.weight), b=_f32(m.norm.bias),
@@ -304,8 +311,14 @@ class _TransformerFn(torch.autograd.Function):
         h16 = ops.cast_f16(h3)
         out = ops.linear(h16, pk["wo"], pk["bo"], residual=x.view(B * L, C), out_dtype=F32, stats_rows_per_img=L,
                          f16_copy=f16_copy)
+        return out, (x, mr0, hn, h0, n1, qkv, o, h1, n2, q2, c2d, kv, o2, h2, n3, gg, h16)
+
+    @staticmethod
+    def forward(ctx, m, f16_copy, box, x, ctx16, *params):
+        out, saved = _TransformerFn.run(m, f16_copy, x, ctx16)
         ctx.m = m
-        ctx.saved = (x, mr0, hn, h0, n1, qkv, o, h1, n2, q2, c2d, kv, o2, h2, n3, gg, h16)
+        ctx.saved, ctx.inputs = (None, (f16_copy, x, ctx16)) if box.get("ckpt") else (saved, None)
+        B, H, W, C = x.shape
         res = out.view(B, H, W, C)
         for k in ("_cs", "_h16"):
             v = getattr(out, k, None)
@@ -317,7 +330,8 @@ class _TransformerFn(torch.autograd.Function):
     def backward(ctx, dout):
         m = ctx.m
         blk = m.transformer_blocks[0]
-        x, mr0, hn, h0, n1, qkv, o, h1, n2, q2, c2d, kv, o2, h2, n3, gg, h16 = ctx.saved
+        saved = ctx.saved if ctx.saved is not None else _TransformerFn.run(m, *ctx.inputs)[1]
+        x, mr0, hn, h0, n1, qkv, o, h1, n2, q2, c2d, kv, o2, h2, n3, gg, h16 = saved
         pk, bp = m._pk._val, blk._packed()
         B, H, W, C = x.shape
         L, heads, scale = H * W, blk.heads, 64 ** -0.5
@@ -383,8 +397,8 @@ class _TransformerFn(torch.autograd.Function):
         return (None, None, None, dx, None, *grads)
 
 
-def transformer(m, x, ctx16, f16_copy=False):
-    box = {}
+def transformer(m, x, ctx16, f16_copy=False, ckpt=False):
+    box = {"ckpt": ckpt}
     return _attach(_TransformerFn.apply(m, f16_copy, box, x, ctx16, *_transformer_params(m)), box)
 
 

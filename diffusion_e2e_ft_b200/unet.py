@@ -258,6 +258,7 @@ class B200UNet2DConditionModel(nn.Module):
         """Same graph as `forward`, every block executed as a torch.autograd.Function (autograd_blocks.py) so
         `loss.backward()` fills `.grad` of the parameters exactly like the reference's training/train.py:563."""
         from . import autograd_blocks as ab
+        ck = bool(self._gradient_checkpointing)
         if self.stream_dtype != F32:
             raise NotImplementedError("training runs with the fp32 residual stream (stream_dtype=torch.float32)")
         cfg = self.config
@@ -284,24 +285,24 @@ class B200UNet2DConditionModel(nn.Module):
         for blk in self.down_blocks:
             for i, r in enumerate(blk.resnets):
                 last = (i == len(blk.resnets) - 1) and blk.downsamplers is not None
-                x = ab.resnet(r, x, temb_of[id(r)], None, f16_copy=last and blk.attentions is None)
+                x = ab.resnet(r, x, temb_of[id(r)], None, f16_copy=last and blk.attentions is None, ckpt=ck)
                 if blk.attentions is not None:
-                    x = ab.transformer(blk.attentions[i], x, ctx16, f16_copy=last)
+                    x = ab.transformer(blk.attentions[i], x, ctx16, f16_copy=last, ckpt=ck)
                 skips.append(x)
             if blk.downsamplers is not None:
                 x = ab.downsample(blk.downsamplers[0], x)
                 skips.append(x)
         mb = self.mid_block
-        x = ab.resnet(mb.resnets[0], x, temb_of[id(mb.resnets[0])])
-        x = ab.transformer(mb.attentions[0], x, ctx16)
-        x = ab.resnet(mb.resnets[1], x, temb_of[id(mb.resnets[1])])
+        x = ab.resnet(mb.resnets[0], x, temb_of[id(mb.resnets[0])], ckpt=ck)
+        x = ab.transformer(mb.attentions[0], x, ctx16, ckpt=ck)
+        x = ab.resnet(mb.resnets[1], x, temb_of[id(mb.resnets[1])], ckpt=ck)
         for blk in self.up_blocks:
             for i, r in enumerate(blk.resnets):
                 skip = skips.pop()
                 last = (i == len(blk.resnets) - 1) and blk.upsamplers is not None and not forward_size
-                x = ab.resnet(r, x, temb_of[id(r)], skip, f16_copy=last and blk.attentions is None)
+                x = ab.resnet(r, x, temb_of[id(r)], skip, f16_copy=last and blk.attentions is None, ckpt=ck)
                 if blk.attentions is not None:
-                    x = ab.transformer(blk.attentions[i], x, ctx16, f16_copy=last)
+                    x = ab.transformer(blk.attentions[i], x, ctx16, f16_copy=last, ckpt=ck)
             if blk.upsamplers is not None:
                 x = ab.upsample(blk.upsamplers[0], x, tuple(skips[-1].shape[1:3]) if forward_size else None)
         if not hasattr(self, "_conv_out_run") or self._conv_out_run.conv is not self.conv_out:

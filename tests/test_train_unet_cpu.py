@@ -93,3 +93,21 @@ def test_geowizard_joint_attention_backward_wiring(emulated):
     assert not r["missing"], r["missing"]
     assert r["forward"] <= 3e-3, r
     assert r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2, r
+
+
+def test_gradient_checkpointing_gives_identical_gradients(emulated):
+    """unet.enable_gradient_checkpointing() (training/train.py:358-359): resnet / transformer blocks keep only their
+    inputs and re-run their forward kernels inside backward — same kernels on the same inputs, so bit-identical."""
+    import make_golden as MG
+    import torch
+    unet_ref, _ = MG.build_tiny()
+    grads = []
+    for ck in (False, True):
+        unet, _ = EC.engine_from_oracle(unet_ref, None, "cpu")
+        unet.requires_grad_(True)
+        if ck:
+            unet.enable_gradient_checkpointing()
+        y = unet(MG.inputs(1, 2, 8, 16, 16), 999, MG.inputs(2, 2, 77, 128, scale=0.5)).sample
+        (y * MG.inputs(7, 2, 4, 16, 16)).sum().backward()
+        grads.append({n: p.grad.clone() for n, p in unet.named_parameters()})
+    assert all(torch.equal(grads[0][n], grads[1][n]) for n in grads[0])
