@@ -11,6 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
 def geowizard_backward():
@@ -36,7 +37,27 @@ def _wgrad_mode(padded, split):
     return ok and not r["missing"] and r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2
 
 
+def checkpointing():
+    import torch
+    import engine_checks as EC
+    import make_golden as MG
+    unet_ref, _ = MG.build_tiny()
+    grads = []
+    for ck in (False, True):
+        unet, _ = EC.engine_from_oracle(unet_ref, None, "cuda:0")
+        unet.requires_grad_(True)
+        if ck:
+            unet.enable_gradient_checkpointing()
+        y = unet(MG.inputs(1, 2, 8, 16, 16).cuda(), 999, MG.inputs(2, 2, 77, 128, scale=0.5).cuda()).sample
+        (y * MG.inputs(7, 2, 4, 16, 16).cuda()).sum().backward()
+        grads.append({n: p.grad.clone() for n, p in unet.named_parameters()})
+    worst = max(EC.rel_l2(grads[1][n], grads[0][n]) for n in grads[0])
+    print("checkpointing: worst rel diff", worst)      # atomics make the GN sums order-dependent: tiny, not zero
+    return worst < 1e-4
+
+
 CHECKS = {
+    "checkpointing": checkpointing,
     "geowizard_backward": geowizard_backward,
     "wgrad_padded": lambda: _wgrad_mode(True, 0),
     "wgrad_split_k": lambda: _wgrad_mode(False, 296),
