@@ -99,10 +99,17 @@ class FlatTrainer:
         loss, _ = e2e_ft_loss(unet, vae, scheduler, rgb, gt, mask, empty_encoding, "depth")
         tr.backward(loss)            # (loss * LOSS_SCALE / accumulation_steps).backward()
         tr.step()                    # all-reduce, clip, AdamW, zero the gradient buffer
-    """
+
+    Data parallel (one process per GPU, `torch.distributed` initialised): the flat gradient is cut into buckets of
+    `bucket_mb`; a bucket's SUM all-reduce is launched asynchronously (NCCL stream) the moment autograd has
+    accumulated its last parameter, i.e. it overlaps the rest of the backward pass — the reference gets the same
+    from accelerate's DDP (train.py:470).  The 1/world_size of the average is folded into the optimizer kernel's
+    unscale factor, so no extra pass over the 3.46 GB buffer.  `backward(loss, sync=False)` skips the exchange on
+    the non-final micro-steps of a gradient accumulation (DDP `no_sync`)."""
 
     def __init__(self, module, lr=3e-5, weight_decay=1e-2, max_grad_norm=1.0, accumulation_steps=1, group=None,
-                 loss_scale=LOSS_SCALE):
+                 loss_scale=LOSS_SCALE, bucket_mb=256):
+        import torch.distributed as dist
         ps = [p for p in module.parameters() if p.requires_grad]
         if not ps:
             raise ValueError("no trainable parameters")
@@ -113,27 +120,69 @@ class FlatTrainer:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        off = 0
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        # buckets: contiguous ranges of the flat buffer in parameter order (backward fills them back to front)
+        cap = max(1, int(bucket_mb * 2 ** 20 / 4))
+        self._buckets, self._bucket_of = [], {}
+        off = start = count = 0
         with torch.no_grad():
-            for p, n in zip(ps, sizes):
+            for idx, (p, n) in enumerate(zip(ps, sizes)):
                 if p.dtype != torch.float32:
                     raise TypeError("FlatTrainer expects fp32 master parameters")
                 view = self.flat_param[off:off + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+                self._bucket_of[id(p)] = len(self._buckets)
                 off += n
+                count += 1
+                if off - start >= cap or idx == len(ps) - 1:
+                    self._buckets.append(dict(lo=start, hi=off, n=count))
+                    start, count = off, 0
         self.params, self.step_count = ps, 0
         self.lr, self.weight_decay, self.max_grad_norm = lr, weight_decay, max_grad_norm
         self.accumulation_steps, self.group, self.loss_scale = accumulation_steps, group, loss_scale
+        self._sync, self._ready, self._handles = True, [0] * len(self._buckets), {}
+        if self.world > 1:
+            for p in ps:
+                p.register_post_accumulate_grad_hook(self._on_grad)
 
-    def backward(self, loss):
+    # autograd calls this right after it has added a parameter's gradient into its view of the flat buffer
+    def _on_grad(self, p):
+        if not self._sync:
+            return
+        b = self._bucket_of[id(p)]
+        self._ready[b] += 1
+        if self._ready[b] == self._buckets[b]["n"]:
+            self._launch(b)
+
+    def _launch(self, b):
+        import torch.distributed as dist
+        bk = self._buckets[b]
+        self._handles[b] = dist.all_reduce(self.flat_grad[bk["lo"]:bk["hi"]], op=dist.ReduceOp.SUM, group=self.group,
+                                           async_op=True)
+
+    def backward(self, loss, sync=True):
+        self._sync = sync
+        self._ready = [0] * len(self._buckets)
         (loss * (self.loss_scale / self.accumulation_steps)).backward()
 
     def step(self, lr=None):
         self.step_count += 1
-        nsq = optimizer_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
-                              lr=self.lr if lr is None else lr, weight_decay=self.weight_decay,
-                              max_grad_norm=self.max_grad_norm, group=self.group, grad_unscale=1.0 / self.loss_scale)
+        unscale = 1.0 / self.loss_scale
+        if self.world > 1:
+            for b in range(len(self._buckets)):                    # parameters without a gradient this step
+                if b not in self._handles:
+                    self._launch(b)
+            for h in self._handles.values():
+                h.wait()
+            self._handles = {}
+            unscale /= self.world                                  # SUM -> mean, folded into the optimizer kernel
+        from .modules import bump_weights_epoch
+        nsq = ops.grad_norm_sq(self.flat_grad)
+        ops.adamw_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                       lr=self.lr if lr is None else lr, weight_decay=self.weight_decay, grad_norm_sq_t=nsq,
+                       max_grad_norm=self.max_grad_norm, grad_unscale=unscale)
+        bump_weights_epoch()
         self.flat_grad.zero_()
         return nsq

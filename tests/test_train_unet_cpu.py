@@ -61,15 +61,21 @@ dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29587", rank=r, wor
 unet_ref, vae_ref = MG.build_tiny()
 unet, vae = E.engine_from_oracle(unet_ref, vae_ref, "cpu")
 unet.requires_grad_(True)
-tr = FlatTrainer(unet, lr=1e-4)
+tr = FlatTrainer(unet, lr=1e-4, bucket_mb=0.25)               # many buckets: async all-reduce per bucket
+assert len(tr._buckets) > 4
 g = torch.Generator().manual_seed(100 + r)                     # different images on each rank
 rgb = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
 gt = torch.rand(1, 1, 64, 64, generator=g) * 9.9 + 0.1
 mask = torch.rand(1, 1, 64, 64, generator=g) > 0.2
 ctx = MG.inputs(5, 1, 77, 128, scale=0.5)
 loss, _ = e2e_ft_loss(unet, vae, DDIMScheduler(), rgb, gt, mask, ctx, "depth")
-tr.backward(loss)
+before = tr.flat_param.clone()
+# the local (pre-exchange) gradient: same micro-step without the exchange, on a scratch copy of the buffer
+tr.backward(loss, sync=False)
 local = tr.flat_grad.clone()
+tr.flat_grad.zero_()
+loss, _ = e2e_ft_loss(unet, vae, DDIMScheduler(), rgb, gt, mask, ctx, "depth")
+tr.backward(loss)                                             # buckets all-reduce while backward is still running
 tr.step()
 both = [torch.zeros_like(tr.flat_param) for _ in range(2)]
 dist.all_gather(both, tr.flat_param)
@@ -77,6 +83,12 @@ assert torch.equal(both[0], both[1]), "ranks diverged"
 grads = [torch.zeros_like(local) for _ in range(2)]
 dist.all_gather(grads, local)
 assert not torch.allclose(grads[0], grads[1]), "ranks saw the same data"
+# expected update: AdamW (emulated kernel contract) on the mean of the two local gradients
+mean = (grads[0] + grads[1]) / 2
+m, v = torch.zeros_like(mean), torch.zeros_like(mean)
+cpu_emulation.adamw_step(before, mean, m, v, 1, lr=1e-4, grad_norm_sq_t=cpu_emulation.grad_norm_sq(mean),
+                         max_grad_norm=1.0, grad_unscale=1.0 / tr.loss_scale)
+assert torch.allclose(before, tr.flat_param, rtol=0, atol=2e-7), (before - tr.flat_param).abs().max()
 print("OK", float(loss))
 ''' % (root, root, root)
     ps = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
