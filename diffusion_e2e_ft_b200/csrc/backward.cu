@@ -127,8 +127,8 @@ __global__ void col_sum_kernel(const T* __restrict__ x, long long rows, int C, l
 // ------------------------------------------------------------------------------------------ GroupNorm bwd
 // mr[n][g] = (mean, rstd) from the forward's statistics: fp64 group sums, or per-channel fp32 sums of the one
 // or two (channel-concatenated) inputs written by the producing kernels' epilogues.
-__global__ void gn_mean_rstd_kernel(const double* __restrict__ sums, const float* __restrict__ cs1, int C1,
-                                    const float* __restrict__ cs2, int C2, int NB, int HW, int groups, float eps,
+__global__ void gn_mean_rstd_kernel(const double* __restrict__ sums, const double* __restrict__ cs1, int C1,
+                                    const double* __restrict__ cs2, int C2, int NB, int HW, int groups, float eps,
                                     float* __restrict__ mr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NB * groups) return;
@@ -140,7 +140,7 @@ __global__ void gn_mean_rstd_kernel(const double* __restrict__ sums, const float
     sq = sums[2 * (long long)i + 1];
   } else {
     for (int c = g * cg; c < (g + 1) * cg; ++c) {
-      const float* src = c < C1 ? cs1 + ((long long)n * C1 + c) * 2 : cs2 + ((long long)n * C2 + (c - C1)) * 2;
+      const double* src = c < C1 ? cs1 + ((long long)n * C1 + c) * 2 : cs2 + ((long long)n * C2 + (c - C1)) * 2;
       su += (double)src[0];
       sq += (double)src[1];
     }
@@ -639,7 +639,7 @@ extern "C" int b200_col_sum(const void* x, int in_f32, long long rows, int C, lo
   return 0;
 }
 
-extern "C" int b200_group_norm_mean_rstd(const double* sums, const float* cs1, int C1, const float* cs2, int C2,
+extern "C" int b200_group_norm_mean_rstd(const double* sums, const double* cs1, int C1, const double* cs2, int C2,
                                          int NB, int HW, int groups, float eps, float* mean_rstd, void* stream) {
   B200_CHECK_ARG(mean_rstd && NB > 0 && HW > 0 && groups > 0 && C1 > 0, "b200_group_norm_mean_rstd: bad arguments");
   B200_CHECK_ARG(sums || cs1, "b200_group_norm_mean_rstd: need group sums or per-channel sums");

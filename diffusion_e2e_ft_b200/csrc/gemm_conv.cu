@@ -155,7 +155,7 @@ extern "C" const char* b200_last_error_string(void) { return b200::last_error();
 extern "C" void b200_debug_force_block_n(int bn) { b200::g_force_bn = bn; }
 extern "C" void b200_debug_set_flags(int f) { b200::g_debug = f; }
 extern "C" void b200_debug_set_swap(int m) { b200::g_swap_mode = m; }
-extern "C" int b200_abi_version(void) { return 1; }
+extern "C" int b200_abi_version(void) { return 2; }
 // Tile width used by the GEGLU epilogue for a packed width N (= 2 x output width); weights must be
 // packed per tile as [value half | gate half] with this width.
 extern "C" int b200_geglu_block_n(int N) {
@@ -167,7 +167,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
                            const float* bias, int bias_row, const void* residual, long long ld_res,
                            long long res_batch_stride, void* out, long long ldo,
                            long long out_batch_stride, int out_f32, int act, float alpha,
-                           float* chan_stats, int rows_per_img, void* out2_f16, int res_mul, void* stream) {
+                           double* chan_stats, int rows_per_img, void* out2_f16, int res_mul, void* stream) {
   B200_CHECK_ARG(A && W && out, "b200_linear: null pointer");
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "b200_linear: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
   B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "b200_linear: lda/ldw must be multiples of 8 elements (16 B)");
@@ -277,7 +277,7 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
                                 const int* tap_dx, int stride, int Ho, int Wo, int out_mul, int out_oy,
                                 int out_ox, const float* bias, const float* rowvec,
                                 long long ld_rowvec, const void* residual, void* out, int out_f32,
-                                int out_nchw, int act, float* chan_stats, void* out2_f16, void* stream) {
+                                int out_nchw, int act, double* chan_stats, void* out2_f16, void* stream) {
   B200_CHECK_ARG(X && Wp && out, "b200_conv2d_nhwc: null pointer");
   B200_CHECK_ARG(Cin % 64 == 0, "b200_conv2d_nhwc: Cin=%d must be a multiple of 64 (use im2col path)", Cin);
   B200_CHECK_ARG(C2 % 64 == 0, "b200_conv2d_nhwc: C2=%d must be a multiple of 64", C2);

@@ -62,7 +62,8 @@ struct GemmParams {
   int act;
   float alpha;                 // scale applied to the accumulator before bias
   __half* out2;                // optional second output: fp16 copy of `out` (same layout) for a following GEMM/conv operand
-  float* chan_stats;           // optional [img][N][2] per-channel (sum, sum of squares) of the stored values
+  double* chan_stats;          // optional [img][N][2] per-channel (sum, sum of squares) of the stored values: shifted
+                               // fp32 partial sums per thread (no cancellation for |mean| >> std), fp64 atomics
   int rows_per_img;            // LINEAR + chan_stats: img = row / rows_per_img (tiles never straddle images)
   int debug;                   // perf experiments: 1 = no epilogue stores, 2 = no A loads, 4 = no B loads, 8 = no MMAs, 16 = empty epilogue
 };
@@ -338,7 +339,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const OutT* __restrict__ res_b = res ? res + (long long)b * p.res_batch_stride + ch : nullptr;
         __half* __restrict__ out2_b = p.out2 ? p.out2 + (long long)b * p.out_batch_stride + ch : nullptr;
         if (!p.conv && p.chan_stats) img = (int)(((long long)m_blk * BLOCK_N) / p.rows_per_img);
-        float st1 = 0.f, st2 = 0.f;
+        float st1 = 0.f, st2 = 0.f, st_shift = 0.f;     // sums of (v - shift), (v - shift)^2 over this thread's pixels
+        int st_cnt = 0;
 
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -407,19 +409,23 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             if (p.chan_stats) {
+              if (c == eg * 32) st_shift = (float)(OutT)vals[0];      // any finite value near the data works as the shift
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float vr = (roff[j] != 0xFFFFFFFFu) ? (float)(OutT)vals[j] : 0.f;
-                st1 += vr;
-                st2 = fmaf(vr, vr, st2);
+                const bool ok = roff[j] != 0xFFFFFFFFu;
+                const float d = ok ? (float)(OutT)vals[j] - st_shift : 0.f;
+                st1 += d;
+                st2 = fmaf(d, d, st2);
+                st_cnt += ok ? 1 : 0;
               }
             }
           }
         }
-        if (p.chan_stats && ch_ok) {
-          float* dst = p.chan_stats + ((long long)img * p.N + ch) * 2;
-          atomicAdd(dst, st1);
-          atomicAdd(dst + 1, st2);
+        if (p.chan_stats && ch_ok && st_cnt) {
+          double* dst = p.chan_stats + ((long long)img * p.N + ch) * 2;
+          const double sh = (double)st_shift, n = (double)st_cnt, s1 = (double)st1;
+          atomicAdd(dst, s1 + n * sh);
+          atomicAdd(dst + 1, (double)st2 + 2.0 * sh * s1 + n * sh * sh);
         }
         tc_fence_before();
         __syncwarp();
@@ -603,16 +609,21 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (p.chan_stats) {
             float st1 = 0.f, st2 = 0.f;
+            int st_cnt = 0;
+            const float st_shift = (float)(OutT)vals[0];
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) {
-              const float vr = (roff[rr] != 0xFFFFFFFFu) ? (float)(OutT)vals[rr] : 0.f;
-              st1 += vr;
-              st2 = fmaf(vr, vr, st2);
+              const bool ok = roff[rr] != 0xFFFFFFFFu;
+              const float d = ok ? (float)(OutT)vals[rr] - st_shift : 0.f;
+              st1 += d;
+              st2 = fmaf(d, d, st2);
+              st_cnt += ok ? 1 : 0;
             }
-            if (col_ok) {
-              float* dst = p.chan_stats + ((long long)img * n_out + col) * 2;
-              atomicAdd(dst, st1);
-              atomicAdd(dst + 1, st2);
+            if (col_ok && st_cnt) {
+              double* dst = p.chan_stats + ((long long)img * n_out + col) * 2;
+              const double sh = (double)st_shift, n = (double)st_cnt, s1 = (double)st1;
+              atomicAdd(dst, s1 + n * sh);
+              atomicAdd(dst + 1, (double)st2 + 2.0 * sh * s1 + n * sh * sh);
             }
           }
           __syncwarp();

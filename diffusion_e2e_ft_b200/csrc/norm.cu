@@ -47,18 +47,21 @@ __device__ __forceinline__ float warp_max(float v) {
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ x1, int C1, const T* __restrict__ x2, int C2,
                                 int HW, int groups, int pix_per_cta, double* __restrict__ sums) {
-  extern __shared__ float sm[];   // [2][C]
+  extern __shared__ double smd[];   // [2][C]
   const int C = C1 + C2;
   const int V = C / 8;
   const int n = blockIdx.y;
   const int rpb = blockDim.x / V;
   const int v = threadIdx.x % V;
   const int r = threadIdx.x / V;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) smd[i] = 0.0;
   __syncthreads();
-  float s[8], q[8];
+  // per-thread sums of (x - shift), (x - shift)^2 with shift = the thread's first element of each channel:
+  // no cancellation for |mean| >> std; converted to plain sums in fp64 before merging
+  float s[8], q[8], sh[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = sh[e] = 0.f;
+  int cnt = 0;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
   const int c0 = v * 8;
@@ -67,6 +70,7 @@ __global__ void gn_stats_kernel(const T* __restrict__ x1, int C1, const T* __res
   const int ld = second ? C2 : C1;
   if (r < rpb) {
     int p = p0 + r;
+    if (p < p1) load8(base + (long long)p * ld, sh);
     for (; p + 3 * rpb < p1; p += 4 * rpb) {
       float f[4][8];
 #pragma unroll
@@ -74,27 +78,33 @@ __global__ void gn_stats_kernel(const T* __restrict__ x1, int C1, const T* __res
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { s[e] += f[u][e]; q[e] += f[u][e] * f[u][e]; }
+        for (int e = 0; e < 8; ++e) { const float d = f[u][e] - sh[e]; s[e] += d; q[e] = fmaf(d, d, q[e]); }
+      cnt += 4;
     }
     for (; p < p1; p += rpb) {
       float f[8];
       load8(base + (long long)p * ld, f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] += f[e] * f[e]; }
+      for (int e = 0; e < 8; ++e) { const float d = f[e] - sh[e]; s[e] += d; q[e] = fmaf(d, d, q[e]); }
+      cnt += 1;
     }
+    if (cnt) {
+      const double nn = (double)cnt;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sm[c0 + e], s[e]);
-      atomicAdd(&sm[C + c0 + e], q[e]);
+      for (int e = 0; e < 8; ++e) {
+        const double shd = (double)sh[e], s1 = (double)s[e];
+        atomicAdd(&smd[c0 + e], s1 + nn * shd);
+        atomicAdd(&smd[C + c0 + e], (double)q[e] + 2.0 * shd * s1 + nn * shd * shd);
+      }
     }
   }
   __syncthreads();
   const int cg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int c = g * cg; c < (g + 1) * cg; ++c) { a += sm[c]; b += sm[C + c]; }
-    atomicAdd(&sums[((long long)n * groups + g) * 2 + 0], (double)a);
-    atomicAdd(&sums[((long long)n * groups + g) * 2 + 1], (double)b);
+    double a = 0.0, b = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) { a += smd[c]; b += smd[C + c]; }
+    atomicAdd(&sums[((long long)n * groups + g) * 2 + 0], a);
+    atomicAdd(&sums[((long long)n * groups + g) * 2 + 1], b);
   }
 }
 
@@ -103,7 +113,7 @@ __global__ void gn_stats_kernel(const T* __restrict__ x1, int C1, const T* __res
 template <typename T>
 __global__ void gn_apply_kernel(const T* __restrict__ x1, int C1, const T* __restrict__ x2, int C2,
                                 int HW, int groups, int pix_per_cta, const double* __restrict__ sums,
-                                const float* __restrict__ cs1, const float* __restrict__ cs2,
+                                const double* __restrict__ cs1, const double* __restrict__ cs2,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 float eps, int silu, __half* __restrict__ y, __half* __restrict__ raw) {
   extern __shared__ float sm[];   // scale[C], shift[C], then group (mean, rstd)[groups][2]
@@ -122,9 +132,9 @@ __global__ void gn_apply_kernel(const T* __restrict__ x1, int C1, const T* __res
       // per-channel sums written by the producing kernels' epilogues; a group may straddle the concat
       su = 0.0; sq = 0.0;
       for (int c = g * cg; c < (g + 1) * cg; ++c) {
-        const float* src = c < C1 ? cs1 + ((long long)n * C1 + c) * 2 : cs2 + ((long long)n * C2 + (c - C1)) * 2;
-        su += (double)src[0];
-        sq += (double)src[1];
+        const double* src = c < C1 ? cs1 + ((long long)n * C1 + c) * 2 : cs2 + ((long long)n * C2 + (c - C1)) * 2;
+        su += src[0];
+        sq += src[1];
       }
     }
     const double mean = su / cnt;
@@ -301,9 +311,42 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, 
   }
 }
 
+// ------------------------------------------------------------------------------ grouped softmax
+// Constant-context cross-attention: logits [rows][ld_in] fp32 hold heads x S scores per query
+// row (column j = head * S + s); softmax over the S keys of each head -> fp16 [rows][ld_out], padding columns
+// (>= heads*S) written as zeros so the row is a K-padded GEMM operand.  One thread per row.
+__global__ void softmax_groups_kernel(const float* __restrict__ lg, int ld_in, long long rows, int heads, int S,
+                                      __half* __restrict__ p, int ld_out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* src = lg + r * ld_in;
+  __half* dst = p + r * ld_out;
+  const int J = heads * S;
+  for (int h = 0; h < heads; ++h) {
+    float m = -INFINITY;
+    for (int s = 0; s < S; ++s) m = fmaxf(m, src[h * S + s]);
+    float sum = 0.f;
+    for (int s = 0; s < S; ++s) sum += __expf(src[h * S + s] - m);
+    const float inv = 1.0f / sum;
+    for (int s = 0; s < S; ++s) dst[h * S + s] = __float2half_rn(__expf(src[h * S + s] - m) * inv);
+  }
+  for (int j = J; j < ld_out; ++j) dst[j] = __float2half_rn(0.f);
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_softmax_groups(const float* logits, int ld_in, long long rows, int heads, int S, void* P,
+                                   int ld_out, void* stream) {
+  B200_CHECK_ARG(logits && P && rows > 0 && heads > 0 && S > 0, "b200_softmax_groups: bad arguments");
+  B200_CHECK_ARG(heads * S <= ld_in && heads * S <= ld_out, "b200_softmax_groups: heads*S=%d exceeds ld (%d, %d)",
+                 heads * S, ld_in, ld_out);
+  softmax_groups_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      logits, ld_in, rows, heads, S, (__half*)P, ld_out);
+  B200_CHECK_LAUNCH("softmax_groups_kernel");
+  return 0;
+}
 
 static int gn_common_check(const char* fn, const void* x1, int C1, const void* x2, int C2, int NB,
                            int HW, int groups) {
@@ -333,7 +376,7 @@ extern "C" int b200_group_norm_stats(const void* x1, int C1, const void* x2, int
   const int T = gn_block(C);
   const int ppc = gn_chunks(NB, HW, T / (C / 8));
   dim3 grid((HW + ppc - 1) / ppc, NB);
-  const size_t smem = 2 * C * sizeof(float);
+  const size_t smem = 2 * C * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
   if (in_f32)
     gn_stats_kernel<float><<<grid, T, smem, st>>>((const float*)x1, C1, (const float*)x2, C2, HW, groups, ppc, sums);
@@ -366,8 +409,8 @@ extern "C" int b200_group_norm_apply(const void* x1, int C1, const void* x2, int
   return 0;
 }
 
-extern "C" int b200_group_norm_apply_cs(const void* x1, int C1, const float* cs1, const void* x2, int C2,
-                                        const float* cs2, int in_f32, int NB, int HW, int groups,
+extern "C" int b200_group_norm_apply_cs(const void* x1, int C1, const double* cs1, const void* x2, int C2,
+                                        const double* cs2, int in_f32, int NB, int HW, int groups,
                                         const float* gamma, const float* beta, float eps, int silu, void* y,
                                         void* raw_copy, void* stream) {
   int r = gn_common_check("b200_group_norm_apply_cs", x1, C1, x2, C2, NB, HW, groups);

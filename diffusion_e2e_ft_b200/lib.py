@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200_e2eft.so")
 
 _lib = None
+ABI_VERSION = 2          # bumped with every signature change of include/b200_e2eft.h
 
 _P = c_void_p
 _LL = c_longlong
@@ -37,6 +38,7 @@ _SIGS = {
     "b200_attention_d64": (c_int, [_P, _LL, _LL, _P, _LL, _LL, _P, _LL, _LL, _P, _LL, _LL, c_int, c_int, c_int,
                                    c_int, c_int, c_float, _P]),
     "b200_softmax_rows": (c_int, [_P, _LL, _P, _LL, _LL, c_int, c_float, _P]),
+    "b200_softmax_groups": (c_int, [_P, c_int, _LL, c_int, c_int, _P, c_int, _P]),
     "b200_upsample_nearest_nhwc": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "b200_timestep_embedding": (c_int, [_P, c_int, c_int, _P, _P]),
     "b200_pointwise_nchw": (c_int, [_P, c_float, _P, c_float, c_int, _P, _P, c_int, c_int, c_int, _LL, _P, _P]),
@@ -75,12 +77,18 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise RuntimeError(f"{LIB_PATH} is missing — run `python -m diffusion_e2e_ft_b200.build`")
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    if not os.path.exists(LIB_PATH) and not build_if_missing:
+        raise RuntimeError(f"{LIB_PATH} is missing — run `python -m diffusion_e2e_ft_b200.build`")
+    if build_if_missing and os.path.exists(_build.NVCC):
+        _build.build()                 # no-op when the source digest matches the stamp: a stale .so is never loaded
+    elif not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing and nvcc is not available to build it")
     lib = ctypes.CDLL(LIB_PATH)
+    lib.b200_abi_version.restype = c_int
+    if lib.b200_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} exports ABI {lib.b200_abi_version()}, this package binds ABI {ABI_VERSION}: "
+                           "rebuild with `python -m diffusion_e2e_ft_b200.build --force`")
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res

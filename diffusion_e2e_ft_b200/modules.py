@@ -241,6 +241,40 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim, eps=1e-5)
         self.ff = FeedForward(dim)
         self._pk = Packed()
+        self._pk_ctx = Packed()
+
+    # Exact single-step specialisation: when every image attends to the SAME context tokens
+    # (marigold_pipeline.py:428-432 repeats one [1,2,1024] empty-text embedding over the batch) the keys / values are
+    # constants of (weights, context), so  softmax(q K^T) V W_o^T  with q = LN(h) W_q^T  collapses to two skinny GEMMs
+    #     logits = LN(h) . A^T,   A[h*S+s] = scale * W_q[head h]^T k_{h,s}            [heads*S, C]
+    #     out    = P . VW,        VW[h*S+s] = W_o[:, head h] v_{h,s}                   [heads*S, C]
+    # instead of a C x C query GEMM, a 128-wide flash tile over 2 keys and a C x C output GEMM.  A and VW are folded
+    # in fp32 once per (weights, context) and cached.
+    CONST_CTX_MAX_J = 64
+
+    def _packed_const_ctx(self, ctx1):
+        """ctx1: [S, Dctx] (any float dtype) -> dict(a16 [Jp, C], vwt16 [C, Jp], J, Jp, S)."""
+        a2 = self.attn2
+        params = [a2.to_q.weight, a2.to_k.weight, a2.to_v.weight, a2.to_out[0].weight, ctx1]
+
+        def build():
+            C, heads = self.dim, self.heads
+            S = ctx1.shape[0]
+            J = heads * S
+            Jp = (J + 7) // 8 * 8
+            c = ctx1.detach().to(F32)
+            k = (c @ a2.to_k.weight.detach().to(F32).t()).view(S, heads, 64)           # [S, heads, 64]
+            v = (c @ a2.to_v.weight.detach().to(F32).t()).view(S, heads, 64)
+            wq = a2.to_q.weight.detach().to(F32).view(heads, 64, C)                    # rows of W_q per head
+            wo = a2.to_out[0].weight.detach().to(F32).view(C, heads, 64)               # columns of W_o per head
+            A = torch.einsum("shd,hdc->hsc", k, wq).reshape(J, C) * (64 ** -0.5)
+            VW = torch.einsum("shd,chd->hsc", v, wo).reshape(J, C)
+            a16 = torch.zeros((Jp, C), dtype=F16, device=c.device)
+            a16[:J] = A.to(F16)
+            vwt16 = torch.zeros((C, Jp), dtype=F16, device=c.device)
+            vwt16[:, :J] = VW.t().to(F16)
+            return dict(a16=a16, vwt16=vwt16, J=J, Jp=Jp, S=S, ctx_ref=ctx1)   # ctx_ref pins the storage the key names
+        return self._pk_ctx.get(params, build)
 
     def _packed(self):
         def build():
@@ -257,8 +291,8 @@ class BasicTransformerBlock(nn.Module):
                 wf=_f16(self.ff.net[2].weight), bf=_f32(self.ff.net[2].bias))
         return self._pk.get(list(self.parameters()), build)
 
-    def run(self, h, B, L, ctx16, sdt=F32):
-        """h: stream [B*L, C]; ctx16: fp16 [B, S, Dctx]."""
+    def run(self, h, B, L, ctx16, sdt=F32, const_ctx=None):
+        """h: stream [B*L, C]; ctx16: fp16 [B, S, Dctx]; const_ctx: [S, Dctx] when all images share one context."""
         pk = self._packed()
         C, heads = self.dim, self.heads
         scale = 64 ** -0.5
@@ -268,11 +302,17 @@ class BasicTransformerBlock(nn.Module):
                               kv_segments=2 if self.joint else 1)
         h = ops.linear(o.view(B * L, C), pk["wo1"], pk["bo1"], residual=h, out_dtype=sdt)
         n2 = ops.layer_norm(h, *pk["ln"][1])
-        q2 = ops.linear(n2, pk["wq2"]).view(B, L, C)
         S = ctx16.shape[1]
-        kv = ops.linear(ctx16.reshape(B * S, -1), pk["wkv2"]).view(B, S, 2 * C)
-        o2 = ops.attention_d64(q2, kv[..., :C], kv[..., C:], heads, scale)
-        h = ops.linear(o2.view(B * L, C), pk["wo2"], pk["bo2"], residual=h, out_dtype=sdt)
+        if const_ctx is not None and heads * S <= self.CONST_CTX_MAX_J:
+            cc = self._packed_const_ctx(const_ctx)
+            lg = ops.linear(n2, cc["a16"], out_dtype=F32)                              # [B*L, Jp] scaled logits
+            p2 = ops.softmax_groups(lg, heads, S, cc["Jp"])
+            h = ops.linear(p2, cc["vwt16"], pk["bo2"], residual=h, out_dtype=sdt)
+        else:
+            q2 = ops.linear(n2, pk["wq2"]).view(B, L, C)
+            kv = ops.linear(ctx16.reshape(B * S, -1), pk["wkv2"]).view(B, S, 2 * C)
+            o2 = ops.attention_d64(q2, kv[..., :C], kv[..., C:], heads, scale)
+            h = ops.linear(o2.view(B * L, C), pk["wo2"], pk["bo2"], residual=h, out_dtype=sdt)
         n3 = ops.layer_norm(h, *pk["ln"][2])
         # GEGLU (attention.py:754-755) as two swapped-operand GEMMs: gate = gelu(x Wg + bg), then
         # value = (x Wv + bv) * gate in the second epilogue (the fused single-GEMM variant is barrier-bound)
@@ -294,7 +334,7 @@ class Transformer2DModel(nn.Module):
         self.proj_out = nn.Linear(dim, dim)
         self._pk = Packed()
 
-    def run(self, x, ctx16, sdt=F32, f16_copy=False):
+    def run(self, x, ctx16, sdt=F32, f16_copy=False, const_ctx=None):
         own = [self.norm.weight, self.norm.bias, self.proj_in.weight, self.proj_in.bias,
                self.proj_out.weight, self.proj_out.bias]
         pk = self._pk.get(own, lambda: dict(g=_f32(self.norm.weight), b=_f32(self.norm.bias),
@@ -305,7 +345,7 @@ class Transformer2DModel(nn.Module):
         hn = ops.group_norm(x, pk["g"], pk["b"], 1e-6, self.groups, False)
         h = ops.linear(hn.view(B * L, C), pk["wi"], pk["bi"], out_dtype=sdt)
         for blk in self.transformer_blocks:
-            h = blk.run(h, B, L, ctx16, sdt)
+            h = blk.run(h, B, L, ctx16, sdt, const_ctx)
         h16 = h if h.dtype == F16 else ops.cast_f16(h)
         out = ops.linear(h16, pk["wo"], pk["bo"], residual=x.view(B * L, C), out_dtype=sdt, stats_rows_per_img=L,
                          f16_copy=f16_copy)
@@ -321,11 +361,17 @@ class ConvInSmall:
         self._pk = Packed()
 
     def run(self, x_nchw, sdt=F32):
+        """x_nchw may carry only the LEADING channels of the layer's input: the missing trailing channels are exact
+        zeros (single-step zeros-noise path, marigold_pipeline.py:418-423,447-449: conv_in on 4 of the 8 channels)."""
         conv = self.conv
-        cin, cout = conv.weight.shape[1], conv.weight.shape[0]
+        cout = conv.weight.shape[0]
+        cin = x_nchw.shape[1]
+        assert cin <= conv.weight.shape[1]
         kpad = (9 * cin + 7) // 8 * 8
-        pk = self._pk.get([conv.weight, conv.bias],
-                          lambda: dict(w=ops.pack_conv_small_cin(conv.weight, kpad), b=_f32(conv.bias)))
+        pks = self.__dict__.setdefault("_pks", {})
+        pk = pks.setdefault(cin, Packed()).get(
+            [conv.weight, conv.bias],
+            lambda: dict(w=ops.pack_conv_small_cin(conv.weight[:, :cin], kpad), b=_f32(conv.bias)))
         NB, _, H, W = x_nchw.shape
         patches = ops.im2col3x3(x_nchw.contiguous(), kpad)
         return _view_cs(ops.linear(patches, pk["w"], pk["b"], out_dtype=sdt, stats_rows_per_img=H * W), NB, H, W, cout)

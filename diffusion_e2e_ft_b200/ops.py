@@ -129,7 +129,7 @@ FUSE_GN_STATS = True     # GroupNorm statistics from the producing GEMM/conv epi
 
 
 def _new_stats(nb, c, device):
-    return torch.zeros((nb, c, 2), dtype=F32, device=device)
+    return torch.zeros((nb, c, 2), dtype=torch.float64, device=device)
 
 
 @_timed("gemm_linear")
@@ -344,6 +344,19 @@ def softmax_rows(s, scale, cols=None):
     p = (torch.zeros if cols != ld else torch.empty)(s.shape, dtype=F16, device=s.device)   # padding stays 0
     _ck(_lib.load().b200_softmax_rows(_p(s), ld, _p(p), ld, rows, cols, float(scale), _stream()),
                "b200_softmax_rows")
+    return p
+
+
+@_timed("softmax_rows")
+def softmax_groups(logits, heads, S, ld_out):
+    """logits fp32 [rows, ld_in] (column head*S+s) -> per-head softmax over the S keys, fp16 [rows, ld_out] with the
+    padding columns zeroed (constant-context cross-attention)."""
+    _need_cuda(logits)
+    assert logits.dtype == F32 and logits.is_contiguous() and logits.dim() == 2
+    rows, ld_in = logits.shape
+    p = torch.empty((rows, ld_out), dtype=F16, device=logits.device)
+    _ck(_lib.load().b200_softmax_groups(_p(logits), ld_in, rows, heads, S, _p(p), ld_out, _stream()),
+        "b200_softmax_groups")
     return p
 
 

@@ -92,8 +92,17 @@ class PipelineBase:
     use_cuda_graph = True
 
     def _weights_key(self):
-        ps = list(self.unet.parameters()) + list(self.vae.parameters())
-        return hash(tuple((p.data_ptr(), p._version) for p in ps))
+        """Identity of every weight a captured graph has baked in: storage pointers + torch version counters of the
+        parameters AND the engine's weights epoch (`modules.bump_weights_epoch`: the flat-buffer optimizer kernel
+        updates parameters with raw device writes that version counters do not see — without the epoch a validation
+        `single_infer` after a training step would replay a graph that points at freed packed-weight buffers)."""
+        from .modules import _WEIGHTS_EPOCH
+        ps = self.__dict__.get("_wk_params")
+        mods = (id(self.unet), id(self.vae), id(getattr(self.unet, "conv_in", None)))
+        if ps is None or self.__dict__.get("_wk_mods") != mods:
+            ps = list(self.unet.parameters()) + list(self.vae.parameters())
+            self.__dict__["_wk_params"], self.__dict__["_wk_mods"] = ps, mods
+        return (_WEIGHTS_EPOCH[0], hash(tuple((p.data_ptr(), p._version) for p in ps)))
 
     def _graphed(self, key, fn, x):
         """Capture `fn(static_x)` once per (key, weights version) and replay it; returns a fresh tensor."""
@@ -256,17 +265,24 @@ class MarigoldPipeline(PipelineBase):
             raise ValueError(f"Unknown noise type: {noise}")
         if self.empty_text_embed is None:
             self.encode_empty_text()
-        ctx = self.empty_text_embed.to(device).repeat((rgb_latent.shape[0], 1, 1))
+        # one context for the whole batch (marigold_pipeline.py:428-432 `.repeat`s it): passed as a broadcast view so
+        # the UNet can take its constant-context cross-attention path (same values, no copy)
+        ctx = self.empty_text_embed.to(device).expand(rgb_latent.shape[0], -1, -1)
         zeros = None
+        spec = getattr(self.unet, "single_step_specialisations", False)
         pt = self.scheduler.config["prediction_type"]
         for i in range(num_inference_steps):
             t, _, a_t, a_prev = self.scheduler.coefficients(i)
-            if latent is None:
-                zeros = torch.zeros_like(rgb_latent) if zeros is None else zeros
-                cur = zeros
+            if latent is None and spec:
+                cur = None
+                unet_input = rgb_latent                               # the zero half is never materialised: conv_in on 4 channels
             else:
-                cur = latent
-            unet_input = torch.cat([rgb_latent, cur], dim=1)          # this order is important (:447-449)
+                if latent is None:
+                    zeros = torch.zeros_like(rgb_latent) if zeros is None else zeros
+                    cur = zeros
+                else:
+                    cur = latent
+                unet_input = torch.cat([rgb_latent, cur], dim=1)      # this order is important (:447-449)
             pred = self.unet(unet_input, t, encoder_hidden_states=ctx).sample
             sa, sb = math.sqrt(a_t), math.sqrt(1.0 - a_t)
             # x0 = c_x * x_t + c_m * model_out  (DDIM, eta = 0)
@@ -283,7 +299,7 @@ class MarigoldPipeline(PipelineBase):
                 dec = self.vae.decode_from_prediction(pred, c_m, noisy=latent, c_noisy=c_x)
                 break
             # intermediate DDIM step (eta = 0): x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps
-            x_t = cur
+            x_t = cur if cur is not None else torch.zeros_like(rgb_latent)
             x0 = c_x * x_t + c_m * pred
             eps = (x_t - sa * x0) / sb
             latent = math.sqrt(a_prev) * x0 + math.sqrt(1.0 - a_prev) * eps

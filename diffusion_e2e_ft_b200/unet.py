@@ -177,21 +177,21 @@ class B200UNet2DConditionModel(nn.Module):
         return self._pk.get(params, build)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, return_dict=True, **unused):
-        ops._need_cuda(sample)                                                      # sm_100a only, no CPU fallback
-        if torch.is_grad_enabled() and (sample.requires_grad or any(p.requires_grad for p in self.parameters())):
-            return self._forward_train(sample, timestep, encoder_hidden_states, class_labels, return_dict)
-        cfg, sdt = self.config, self.stream_dtype
-        B, _, H, W = sample.shape
-        dev = sample.device
-        n_up = len(cfg["block_out_channels"]) - 1
-        forward_size = (H % (2 ** n_up) != 0) or (W % (2 ** n_up) != 0)      # unet_2d_condition.py:920-930
+    # Exact single-step specialisations (SURVEY.md §8 f1) — pure wins on the reference's one-step path, all
+    # parity-tested against the general path (tests/engine_checks.py:run_single_step_specialisations):
+    #   * constant python-scalar timestep and no class labels (marigold_pipeline.py:452: `t` of the 1-step trailing
+    #     schedule is always 999): temb and the 22 stacked `time_emb_proj` outputs are a function of the weights only
+    #     -> computed once per weights version (unet_2d_condition.py:974-981), no embedding kernels per call;
+    #   * zeros noise (marigold_pipeline.py:418-423): `sample` may carry only the leading channels, conv_in runs on
+    #     those (the missing input channels are exact zeros);
+    #   * one context shared by the batch (marigold_pipeline.py:428-432; detected without a device sync as a
+    #     batch-broadcast view, `stride(0) == 0`, or batch 1): cross-attention collapses to two skinny GEMMs
+    #     (modules.BasicTransformerBlock._packed_const_ctx).
+    single_step_specialisations = True
 
-        # ---- time / class embedding (unet_2d_condition.py:957-1000)
-        if not torch.is_tensor(timestep):
-            t = torch.full((B,), float(timestep), dtype=F32, device=dev)
-        else:
-            t = timestep.to(device=dev, dtype=F32).reshape(-1).expand(B).contiguous()
+    def _time_embedding(self, t, class_labels, B, dev):
+        """[B, sum(cout)] fp32: every resnet's time_emb_proj(silu(temb (+class_emb))) (unet_2d_condition.py:957-1000)."""
+        cfg = self.config
         ep = self._embed_packed()
         e = ops.timestep_embedding(t, cfg["block_out_channels"][0])
         e = ops.linear(e, ep["w1"], ep["b1"], act=ops.ACT_SILU)
@@ -205,11 +205,46 @@ class B200UNet2DConditionModel(nn.Module):
             e = ops.linear(e, ep["w2"], ep["b2"], residual=c, act=ops.ACT_SILU)     # silu(temb + class_emb)
         else:
             e = ops.linear(e, ep["w2"], ep["b2"], act=ops.ACT_SILU)                 # silu(temb)
-        temb_all = ops.linear(e, ep["wall"], ep["ball"], out_dtype=F32)              # all 22 time_emb_proj at once
+        return ops.linear(e, ep["wall"], ep["ball"], out_dtype=F32)                  # all 22 time_emb_proj at once
+
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, return_dict=True, **unused):
+        ops._need_cuda(sample)                                                      # sm_100a only, no CPU fallback
+        if torch.is_grad_enabled() and (sample.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_train(sample, timestep, encoder_hidden_states, class_labels, return_dict)
+        cfg, sdt = self.config, self.stream_dtype
+        B, _, H, W = sample.shape
+        dev = sample.device
+        n_up = len(cfg["block_out_channels"]) - 1
+        forward_size = (H % (2 ** n_up) != 0) or (W % (2 ** n_up) != 0)      # unet_2d_condition.py:920-930
+        spec = self.single_step_specialisations
+        if sample.shape[1] != cfg["in_channels"] and not (spec and sample.shape[1] < cfg["in_channels"]):
+            raise ValueError(f"sample has {sample.shape[1]} channels, conv_in expects {cfg['in_channels']}")
+
+        # ---- time / class embedding (unet_2d_condition.py:957-1000)
+        ep = self._embed_packed()
+        if spec and not torch.is_tensor(timestep) and self.class_embedding is None:
+            cache = ep.setdefault("temb_cache", {})                 # lives and dies with the packed weights
+            key = (float(timestep), B, str(dev))
+            temb_all = cache.get(key)
+            if temb_all is None:
+                t = torch.full((B,), float(timestep), dtype=F32, device=dev)
+                temb_all = cache[key] = self._time_embedding(t, None, B, dev)
+                if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+                    cache.pop(key)                                   # graph-private memory must not outlive the capture
+        else:
+            if not torch.is_tensor(timestep):
+                t = torch.full((B,), float(timestep), dtype=F32, device=dev)
+            else:
+                t = timestep.to(device=dev, dtype=F32).reshape(-1).expand(B).contiguous()
+            temb_all = self._time_embedding(t, class_labels, B, dev)
         resnets = list(self._resnets())
         temb_of = {id(r): temb_all[:, o:o + r.cout] for r, o in zip(resnets, ep["offs"])}
 
-        ctx16 = encoder_hidden_states.to(F16).contiguous()
+        ehs = encoder_hidden_states
+        const_ctx = None
+        if spec and ehs.dim() == 3 and (ehs.shape[0] == 1 or ehs.stride(0) == 0):
+            const_ctx = ehs[0]                                      # [S, Dctx] shared by every image
+        ctx16 = ehs.to(F16).contiguous()
 
         # ---- down path
         if not hasattr(self, "_conv_in_run") or self._conv_in_run.conv is not self.conv_in:
@@ -221,7 +256,7 @@ class B200UNet2DConditionModel(nn.Module):
                 last = (i == len(blk.resnets) - 1) and blk.downsamplers is not None    # feeds the stride-2 conv
                 x = r.run(x, temb_of[id(r)], None, sdt, f16_copy=last and blk.attentions is None)
                 if blk.attentions is not None:
-                    x = blk.attentions[i].run(x, ctx16, sdt, f16_copy=last)
+                    x = blk.attentions[i].run(x, ctx16, sdt, f16_copy=last, const_ctx=const_ctx)
                 skips.append(x)
             if blk.downsamplers is not None:
                 x = blk.downsamplers[0].run(x, sdt)
@@ -229,7 +264,7 @@ class B200UNet2DConditionModel(nn.Module):
         # ---- mid
         mb = self.mid_block
         x = mb.resnets[0].run(x, temb_of[id(mb.resnets[0])], None, sdt)
-        x = mb.attentions[0].run(x, ctx16, sdt)
+        x = mb.attentions[0].run(x, ctx16, sdt, const_ctx=const_ctx)
         x = mb.resnets[1].run(x, temb_of[id(mb.resnets[1])], None, sdt)
         # ---- up path
         for bi, blk in enumerate(self.up_blocks):
@@ -238,7 +273,7 @@ class B200UNet2DConditionModel(nn.Module):
                 last = (i == len(blk.resnets) - 1) and blk.upsamplers is not None and not forward_size
                 x = r.run(x, temb_of[id(r)], skip, sdt, f16_copy=last and blk.attentions is None)
                 if blk.attentions is not None:
-                    x = blk.attentions[i].run(x, ctx16, sdt, f16_copy=last)
+                    x = blk.attentions[i].run(x, ctx16, sdt, f16_copy=last, const_ctx=const_ctx)
             if blk.upsamplers is not None:
                 size = tuple(skips[-1].shape[1:3]) if forward_size else None
                 x = blk.upsamplers[0].run(x, size, sdt)

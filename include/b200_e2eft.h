@@ -47,8 +47,10 @@ int b200_linear(const void* A, long long lda, long long a_batch_stride,
                 const void* residual, long long ld_res, long long res_batch_stride,
                 void* out, long long ldo, long long out_batch_stride, int out_f32,
                 int act, float alpha,
-                float* chan_stats /* optional [M/rows_per_img][N][2]: per-channel sum / sum of squares of
-                                     the stored values, accumulated with atomics (caller zeroes) */,
+                double* chan_stats /* optional [M/rows_per_img][N][2]: per-channel sum / sum of squares of
+                                      the stored values (caller zeroes): each thread accumulates shifted fp32
+                                      partial sums (no cancellation when |mean| >> std) and merges them with
+                                      fp64 atomics, so the result is order-independent to ~1e-16 */,
                 int rows_per_img,
                 void* out2_f16 /* optional fp16 copy of `out` (same strides) for a following GEMM operand */,
                 int res_mul /* 1: out = act(alpha*acc + bias) * residual (GEGLU as gate GEMM + value GEMM) */,
@@ -75,7 +77,7 @@ int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin,
                      int stride, int Ho, int Wo, int out_mul, int out_oy, int out_ox,
                      const float* bias, const float* rowvec, long long ld_rowvec,
                      const void* residual, void* out, int out_f32, int out_nchw, int act,
-                     float* chan_stats /* optional [NB][Cout][2], see b200_linear */,
+                     double* chan_stats /* optional [NB][Cout][2], see b200_linear */,
                      void* out2_f16 /* optional fp16 NHWC copy of `out` */, void* stream);
 
 /* 3x3 / stride 1 / pad 1 convolution with Cout <= 8 (the `conv_out` layers: unet_2d_condition.py:617-619
@@ -104,9 +106,9 @@ int b200_group_norm_apply(const void* x1, int C1, const void* x2, int C2, int in
                           float eps, int silu, void* y, void* raw_copy, void* stream);
 
 /* Same, but the statistics come from per-channel sums produced by the epilogue of the kernel that wrote
- * each source (chan_stats of b200_linear / b200_conv2d_nhwc): cs1 [NB][C1][2], cs2 [NB][C2][2] (fp32). */
-int b200_group_norm_apply_cs(const void* x1, int C1, const float* cs1, const void* x2, int C2,
-                             const float* cs2, int in_f32, int NB, int HW, int groups,
+ * each source (chan_stats of b200_linear / b200_conv2d_nhwc): cs1 [NB][C1][2], cs2 [NB][C2][2] (fp64). */
+int b200_group_norm_apply_cs(const void* x1, int C1, const double* cs1, const void* x2, int C2,
+                             const double* cs2, int in_f32, int NB, int HW, int groups,
                              const float* gamma, const float* beta, float eps, int silu, void* y,
                              void* raw_copy, void* stream);
 
@@ -131,6 +133,13 @@ int b200_attention_d64(const void* q, long long q_bs, long long q_ls,
 /* Row softmax: P[r][:] = softmax(scale * S[r][:]) fp32 -> fp16 (VAE mid-block attention, d=512). */
 int b200_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows,
                       int cols, float scale, void* stream);
+
+/* Grouped softmax for the constant-context cross-attention specialisation (SURVEY.md §8 f1;
+ * Marigold/marigold/marigold_pipeline.py:428-432 repeats ONE [1,2,1024] empty-text embedding over the batch,
+ * GeoWizard/geowizard/models/attention.py:375-380 attends to it): logits [rows][ld_in] fp32, column
+ * head*S + s; softmax over the S keys of every head -> fp16 [rows][ld_out] (columns >= heads*S zeroed). */
+int b200_softmax_groups(const float* logits, int ld_in, long long rows, int heads, int S, void* P, int ld_out,
+                        void* stream);
 
 /* Nearest-neighbour resize NHWC (in_f32 ? fp32 : fp16) -> fp16 (Upsample2D interpolate,
  * exact 2x or explicit `size=`, unet_2d_condition.py:1185-1186). */
@@ -197,7 +206,7 @@ int b200_adamw_step_scaled(float* param, const float* grad, float* exp_avg, floa
 int b200_gather_planar(const void* x, int in_f32, long long ldx, int NB, int H, int W, int C, int Ho, int Wo, int stride, int up,
                        int oy, int ox, void* out, long long ldo, void* stream);
 int b200_col_sum(const void* x, int in_f32, long long rows, int C, long long ld, float* out, void* stream);
-int b200_group_norm_mean_rstd(const double* sums, const float* cs1, int C1, const float* cs2, int C2, int NB, int HW,
+int b200_group_norm_mean_rstd(const double* sums, const double* cs1, int C1, const double* cs2, int C2, int NB, int HW,
                               int groups, float eps, float* mean_rstd, void* stream);
 int b200_group_norm_bwd_sums(const void* x, int in_f32, int Cx, int c_off, int Ctot, const void* dy, int NB, int HW,
                              int groups, const float* mean_rstd, const float* gamma, const float* beta, int silu,

@@ -183,6 +183,13 @@ def softmax_rows(s, scale, cols=None):
     return p
 
 
+def softmax_groups(logits, heads, S, ld_out):
+    rows = logits.shape[0]
+    p = torch.zeros((rows, ld_out), dtype=F16)
+    p[:, :heads * S] = torch.softmax(logits[:, :heads * S].view(rows, heads, S), dim=-1).reshape(rows, heads * S).half()
+    return p
+
+
 def softmax_bwd_rows(p, dp, scale, cols=None):
     cols = cols or p.shape[-1]
     pf, d = p[..., :cols].float(), dp[..., :cols]
@@ -372,7 +379,7 @@ _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm
                  group_norm_bwd=group_norm_bwd, layer_norm=layer_norm, layer_norm_bwd=layer_norm_bwd,
                  attention_d64=attention_d64, softmax_rows=softmax_rows, softmax_bwd_rows=softmax_bwd_rows,
                  gather_planar=gather_planar, col_sum=col_sum, act_bwd=act_bwd, geglu_bwd=geglu_bwd,
-                 cast_f16=cast_f16, im2col3x3=im2col3x3, conv3x3_small_cout=conv3x3_small_cout,
+                 softmax_groups=softmax_groups, cast_f16=cast_f16, im2col3x3=im2col3x3, conv3x3_small_cout=conv3x3_small_cout,
                  timestep_embedding=timestep_embedding, nhwc_to_nchw_f32=nhwc_to_nchw_f32,
                  pointwise_nchw=pointwise_nchw, decode_post=decode_post, ssi_loss=ssi_loss, angular_loss=angular_loss,
                  ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd, grad_norm_sq=grad_norm_sq, adamw_step=adamw_step,

@@ -87,6 +87,38 @@ def run_marigold_tiny(device="cuda:0", stream_dtype=torch.float32):
 
 
 @torch.no_grad()
+def run_single_step_specialisations(device="cuda:0", hw=(16, 16), full_width=False):
+    """the exact single-step specialisations (cached constant-t embedding, conv_in on the 4 non-zero
+    channels, constant-context cross-attention as two skinny GEMMs) against (a) the engine's own general path on the
+    same inputs and (b) the fp32 oracle."""
+    if full_width:
+        from oracle.unet import UNet2DConditionRef, UNetConfig, seeded_init
+        ref = seeded_init(UNet2DConditionRef(UNetConfig()), seed=4321).eval()
+        dctx = 1024
+    else:
+        ref, _ = MG.build_tiny()
+        dctx = 128
+    unet, _ = engine_from_oracle(ref, None, device)
+    lat = MG.inputs(21, 2, 4, *hw)
+    ctx1 = MG.inputs(22, 1, 2, dctx, scale=0.5)
+    x8 = torch.cat([lat, torch.zeros_like(lat)], 1)
+    want = ref(x8, 999, ctx1.repeat(2, 1, 1)).sample
+    unet.single_step_specialisations = False
+    general = unet(x8.to(device), 999, ctx1.repeat(2, 1, 1).to(device)).sample
+    unet.single_step_specialisations = True
+    ctx_dev = ctx1.to(device)
+    spec = unet(lat.to(device), 999, ctx_dev.expand(2, -1, -1)).sample            # 4-channel sample, broadcast context
+    spec2 = unet(lat.to(device), 999, ctx_dev.expand(2, -1, -1)).sample           # second call: cached tables
+    # a per-image (non-broadcast) context must take the general path and still be right
+    ctx2 = MG.inputs(23, 2, 2, dctx, scale=0.5)
+    want2 = ref(x8, 999, ctx2).sample
+    got2 = unet(x8.to(device), 999, ctx2.to(device)).sample
+    return dict(spec_vs_general=rel_l2(spec, general), spec_vs_oracle=rel_l2(spec, want),
+                general_vs_oracle=rel_l2(general, want), repeat_call=rel_l2(spec2, spec),
+                per_image_ctx_vs_oracle=rel_l2(got2, want2))
+
+
+@torch.no_grad()
 def run_geowizard_tiny(device="cuda:0", stream_dtype=torch.float32):
     gold = torch.load(GOLD)
     gunet_ref, vae_ref = MG.build_tiny("geowizard")

@@ -205,6 +205,43 @@ def check_gn_fused_stats(swap=True, seed=31):
     return rel_l2(out, ref), 6e-4
 
 
+def check_gn_stress(fused=False, NB=1, H=768, W=768, C=128, mean=50.0, std=1.0, seed=41):
+    """per-channel |mean| >> std (mean 50, std 1, 128 ch x 768^2) against an fp64 GroupNorm.
+    A single-pass fp32 sum / sum-of-squares loses the variance to cancellation here (E[x^2] ~ 2501 vs var 1); the
+    kernels accumulate SHIFTED partial sums per thread and merge them in fp64.
+    fused=False: standalone gn_stats pass on an fp32 tensor.  fused=True: statistics from the epilogue of the
+    producing GEMM (a linear layer whose bias carries the large per-channel mean), both tile orientations."""
+    g = _rand(C, seed=seed + 2, dtype=torch.float32) * 0.2 + 1.0
+    b = _rand(C, seed=seed + 3, dtype=torch.float32) * 0.2
+    cmean = (mean * (1.0 + 0.2 * torch.arange(C, device=DEV) / C)).float()                # 50 .. 60 per channel
+    if not fused:
+        x = _rand(NB, H, W, C, seed=seed, dtype=torch.float32) * std + cmean
+        y = ops.group_norm(x, g, b, 1e-5, 32, True)
+        xs = [x]
+    else:
+        K = 64
+        a = _rand(NB * H * W, K, seed=seed)
+        w = _rand(C, K, seed=seed + 1, scale=std / math.sqrt(K))
+        xs, ys = [], []
+        for swap in (1, 0):
+            ops._lib.load().b200_debug_set_swap(swap)
+            try:
+                x = ops.linear(a, w, cmean.contiguous(), out_dtype=torch.float32, stats_rows_per_img=H * W)
+            finally:
+                ops._lib.load().b200_debug_set_swap(1)
+            assert getattr(x, "_cs", None) is not None
+            xv = x.view(NB, H, W, C)
+            xv._cs = x._cs
+            ys.append(ops.group_norm(xv, g, b, 1e-5, 32, True))
+            xs.append(xv)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for x, yy in zip(xs, [y] if not fused else ys):
+        ref = F.silu(F.group_norm(x.double().permute(0, 3, 1, 2), 32, g.double(), b.double(), 1e-5)).permute(0, 2, 3, 1)
+        worst = max(worst, ((yy.double() - ref).norm() / ref.norm()).item())
+    return worst, 6e-4          # fp16 output rounding only (2.8e-4 rms); a cancelled variance shows up as >= 1e-2
+
+
 def check_layer_norm(rows=1000, C=640, in_f32=True, seed=0):
     dt = torch.float32 if in_f32 else torch.float16
     x = _rand(rows, C, seed=seed, dtype=dt) * 2 + 0.3
@@ -454,6 +491,8 @@ CHECKS = {
     "gn_128": lambda: check_group_norm(C1=128, H=64, W=64),
     "gn_fused_stats_swap": lambda: check_gn_fused_stats(True),
     "gn_fused_stats_normal": lambda: check_gn_fused_stats(False),
+    "gn_stress_mean50_standalone": lambda: check_gn_stress(False),
+    "gn_stress_mean50_fused": lambda: check_gn_stress(True),
     "ln_f32": lambda: check_layer_norm(),
     "ln_f16_1280": lambda: check_layer_norm(C=1280, in_f32=False),
     "ln_320": lambda: check_layer_norm(C=320),

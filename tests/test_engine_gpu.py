@@ -34,6 +34,18 @@ def test_marigold_tiny_fp16_stream():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("full_width", [False, True])
+def test_single_step_specialisations_match_general_path(full_width):
+    """cached constant-t embedding + 4-channel conv_in + constant-context cross-attention (two skinny
+    GEMMs) == the general path (fp16-operand tolerance) and the fp32 oracle."""
+    r = EC.run_single_step_specialisations(hw=(24, 24) if full_width else (16, 16), full_width=full_width)
+    print(r)
+    assert r["spec_vs_general"] <= 2e-3 and r["repeat_call"] == 0.0, r
+    assert r["spec_vs_oracle"] <= 3e-3 and r["spec_vs_oracle"] <= 1.15 * r["general_vs_oracle"], r
+    assert r["per_image_ctx_vs_oracle"] <= 3e-3, r
+
+
+@pytest.mark.gpu
 def test_geowizard_tiny_joint_attention_matches_golden():
     r = EC.run_geowizard_tiny()
     print(r)

@@ -21,7 +21,8 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/b200_e2eft.h but not exported"
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
-    assert L.b200_abi_version() == 1
+    from diffusion_e2e_ft_b200.lib import ABI_VERSION
+    assert L.b200_abi_version() == ABI_VERSION
     assert L.b200_geglu_block_n(2560) == 160 and L.b200_geglu_block_n(512) == 256
 
 

@@ -23,6 +23,13 @@ def test_unet_backward_wiring_matches_oracle_autograd(emulated, hw):
     assert r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2, r
 
 
+def test_single_step_specialisations_wiring(emulated):
+    """SURVEY.md §8 f1 host logic (folded A / VW tables, cached embedding, 4-channel conv_in) with emulated kernels."""
+    r = EC.run_single_step_specialisations(device="cpu", hw=(8, 8))
+    assert r["spec_vs_general"] <= 2e-3 and r["spec_vs_oracle"] <= 3e-3 and r["repeat_call"] == 0.0, r
+    assert r["per_image_ctx_vs_oracle"] <= 3e-3, r
+
+
 @pytest.mark.parametrize("modality,tol", [("depth", 3e-2), ("normals", 6e-2)])
 def test_training_micro_step_wiring(emulated, modality, tol):
     r = EC.run_training_step_tiny(device="cpu", modality=modality)

@@ -40,6 +40,15 @@ elif what == "gn":
     x = r(4, 768, 768, 128); gm = torch.ones(128, device=dev); bt = torch.zeros(128, device=dev)
     fn = lambda: ops.group_norm(x, gm, bt, 1e-6)
     flops = 0
+elif what == "gn32":                  # fp32 stream in, fp16 out: the VAE's dominant GroupNorm shape (6 B / element)
+    x = r(4, 768, 768, 128).float(); gm = torch.ones(128, device=dev); bt = torch.zeros(128, device=dev)
+    fn = lambda: ops.group_norm(x, gm, bt, 1e-6)
+    flops = 0
+elif what == "lin320":                # K = 320 GEMM with fp32 residual / output (attention out-proj, proj_out)
+    a = r(73728, 320); w = r(320, 320, sc=0.05); b = torch.zeros(320, device=dev)
+    resid = r(73728, 320).float()
+    fn = lambda: ops.linear(a, w, b, residual=resid, out_dtype=torch.float32)
+    flops = 2 * 73728 * 320 * 320
 elif what == "geglu":
     pass
 elif what == "linear":
