@@ -3,18 +3,23 @@
 
     python bench.py --gpus N --steps K --warmup W            (torchrun launches N>1, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --workload {marigold,normals,geowizard,train} [--res R] [--batch B]      (BASELINE.json configs 2-5)
 
-Workload = BASELINE.json configs[1]: marigold-e2e-ft-depth inference, bs=8 per GPU, fp16 operands,
+Default workload = BASELINE.json configs[1]: marigold-e2e-ft-depth inference, bs=8 per GPU, fp16 operands,
 processing_res=768, 1 denoising step, zeros noise, synthetic 3x768x768 RGB, seeded random weights.
 One "step" = one `MarigoldPipeline.single_infer` over a batch (VAE encode -> UNet -> x0 -> VAE decode
 -> depth post-ops).  Metric: 768x768 depth images / second (whole job, all GPUs).
 
   value      device-timed throughput, inputs resident in HBM
-  e2e        same through the public pipeline API from pinned HOST buffers (H2D + D2H inside the timing)
+  e2e        same through the public pipeline API from pinned fp32 HOST buffers (H2D + D2H inside the timing)
   roofline   implicit-GEMM conv kernel (the dominant kernel): algorithmic FLOPs / CUDA-event time of its
              launches inside the timed region, against the measured bf16 peak (MEASURED_PEAKS.json)
+  train_step BASELINE.json configs[2] (training/train.py:469-568, bs=2 per GPU, 768x768, fp32 masters): forward /
+             backward / optimizer split and the gradient all-reduce (NCCL over NVLink at N > 1) with the bucketed
+             overlap on and off — the one collective of this workload, driver-run at every N
   cpu_baseline / --impl reference: the ORACLE (oracle/, plain PyTorch fp32 restatement of the reference's
-             diffusers path, which is not installable here) on the host cores.
+             diffusers path, which is not installable here) on the host cores, at the REAL config: one 3x768x768
+             image per `single_infer` (BASELINE.json configs[0]), the same fixed resolution in both legs.
 """
 import argparse
 import json
@@ -101,6 +106,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- oracle legs
+CPU_RES = 768                      # BASELINE.json configs[0]: one 3x768x768 image per single_infer — both CPU legs use it
+CPU_BUDGET_S = 150.0               # wall-clock cap of the timed CPU steps (a 768^2 image takes ~20-30 s on the host cores)
+
+
 def build_oracle(seed=1234, full=True):
     """Oracle modules with cheap synthetic weights (timing only): built on the meta device, then filled
     with U(-1/sqrt(fan_in), 1/sqrt(fan_in)) in place (default nn init of 950 M parameters takes ~45 s)."""
@@ -157,14 +166,23 @@ def pick_cpu_threads(unet, vae):
     return best
 
 
-def pick_cpu_res(unet, vae, budget_s_per_step):
-    """Largest resolution whose oracle step fits the per-step budget, from a small calibration run."""
-    t = oracle_step(unet, vae, 128)
-    tf_s = TFLOP_PER_IMAGE[128] / t                           # conservative: small problems run slower
-    for res in (768, 512, 384, 256):
-        if TFLOP_PER_IMAGE[res] / tf_s <= budget_s_per_step:
-            return res
-    return 128
+def cpu_reference_run(steps, warmup, budget_s=CPU_BUDGET_S):
+    """The reference's CPU path (oracle restatement, fp32, PyTorch CPU kernels) at the real config: every step is one
+    `single_infer` of ONE 3x768x768 image.  At most `steps` timed steps, stopped early once `budget_s` is spent (never
+    fewer than one); at most one untimed warm-up."""
+    unet, vae = build_oracle()
+    cores = pick_cpu_threads(unet, vae)
+    n_warm = min(1, warmup)
+    for _ in range(n_warm):
+        oracle_step(unet, vae, CPU_RES)
+    times = []
+    while len(times) < max(1, steps) and (not times or sum(times) + times[-1] <= budget_s):
+        times.append(oracle_step(unet, vae, CPU_RES))
+    dt = sum(times)
+    sample = (f"{len(times)} timed + {n_warm} warm-up oracle single_infer call(s), each ONE 3x{CPU_RES}x{CPU_RES} image "
+              f"(BASELINE.json configs[0]), fp32, {cores} host threads; per image "
+              f"{min(times):.1f}-{max(times):.1f} s; capped at {budget_s:.0f} s of timed CPU work")
+    return dict(value=len(times) / dt, steps=len(times), warmup=n_warm, seconds=dt, cores=cores, sample=sample)
 
 
 def run_reference(args):
@@ -173,59 +191,54 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    unet, vae = build_oracle()
-    cores = pick_cpu_threads(unet, vae)
-    res = pick_cpu_res(unet, vae, 120.0 / max(1, args.steps + args.warmup))
-    for _ in range(args.warmup):
-        oracle_step(unet, vae, res)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_step(unet, vae, res)
-    dt = time.perf_counter() - t0
-    eq_images = args.steps * TFLOP_PER_IMAGE[res] / TFLOP_PER_IMAGE[768]
-    value = eq_images / dt
-    sample = (f"{args.steps} x oracle single_infer of 1 image at {res}x{res} fp32 on {cores} host threads; "
-              f"converted to 768x768-equivalent images by the tensor-FLOP ratio {TFLOP_PER_IMAGE[res]}/{TFLOP_PER_IMAGE[768]}")
+    r = cpu_reference_run(args.steps, args.warmup)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/s", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": r["warmup"], "steps_requested": args.steps,
+        "ms_per_step": r["seconds"] / r["steps"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "marigold-e2e-ft-depth single_infer, 1 step, zeros noise, 768x768 (CPU oracle)",
+        "config": {"workload": "marigold-e2e-ft-depth single_infer, 1 step, zeros noise, one 3x768x768 image per step "
+                               "(CPU oracle = the reference's diffusers graph restated; BASELINE.json configs[0])",
                    "global_batch": 1},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def cpu_baseline_leg(budget_s=20.0):
-    unet, vae = build_oracle()
-    cores = pick_cpu_threads(unet, vae)
-    res = pick_cpu_res(unet, vae, budget_s)
-    t = oracle_step(unet, vae, res)
-    value = (TFLOP_PER_IMAGE[res] / TFLOP_PER_IMAGE[768]) / t
-    return {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"1 oracle single_infer (fp32 PyTorch CPU restatement of the diffusers path) of 1 image at "
-                      f"{res}x{res} in {t:.1f} s, scaled to 768x768-equivalent images by tensor-FLOP ratio"}
+def cpu_baseline_leg():
+    r = cpu_reference_run(1, 0, budget_s=60.0)
+    return {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
 
 # --------------------------------------------------------------------------------------------- engine
-def build_engine(device, stream_dtype, module_dtype, seed=1234):
+def build_engine(device, stream_dtype, module_dtype, workload="marigold", seed=1234):
     import torch
-    from diffusion_e2e_ft_b200 import (B200AutoencoderKL, B200UNet2DConditionModel, DDIMScheduler, MarigoldPipeline)
+    from diffusion_e2e_ft_b200 import (B200AutoencoderKL, B200UNet2DConditionModel, DDIMScheduler,
+                                       DepthNormalEstimationPipeline, MarigoldPipeline)
     torch.manual_seed(seed)
     with torch.device(device):
-        unet = B200UNet2DConditionModel(stream_dtype=stream_dtype)
+        if workload == "geowizard":
+            # SD-2 widths, class-embedding projection (10), 1 x 768 image-embedding token,
+            # joint depth/normal self-attention
+            unet = B200UNet2DConditionModel(stream_dtype=stream_dtype, class_embed_type="projection",
+                                            projection_class_embeddings_input_dim=10, cross_attention_dim=768,
+                                            joint_attention=True)
+        else:
+            unet = B200UNet2DConditionModel(stream_dtype=stream_dtype)
         vae = B200AutoencoderKL(stream_dtype=stream_dtype)
     unet.to(module_dtype).eval().requires_grad_(False)
     vae.to(module_dtype).eval().requires_grad_(False)
+    if workload == "geowizard":
+        return DepthNormalEstimationPipeline(unet, vae, DDIMScheduler())
     ete = (torch.randn(1, 2, 1024, device=device) * 0.5).to(module_dtype)
     return MarigoldPipeline(unet, vae, DDIMScheduler(), empty_text_embed=ete)
 
 
-def run_engine(args):
+def _dist_setup():
+    import datetime
     import torch
     import torch.distributed as dist
-    from diffusion_e2e_ft_b200 import ops
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -234,21 +247,160 @@ def run_engine(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    bs, res = args.batch, args.res
+        # a collective that never completes raises after the timeout instead of hanging the whole bench
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    return world, rank, local, dev
+
+
+def train_leg(dev, rank, world, res=768, batch=2, steps=3, warmup=2, modality="depth"):
+    """BASELINE.json configs[2] / SURVEY.md §8(d) config 3: training/train.py:469-568 step semantics — SD-2 UNet with the
+    8-channel conv_in, fp32 master weights, bs `batch` per GPU, rgb U(-1,1), GT depth U(0.1,10), mask all-true, ctx
+    [1,77,1024], data parallel over `world` ranks (one gradient all-reduce per optimizer step, NCCL over NVLink).
+    Device-timed (CUDA events), max over ranks.  Three timings of the same step: bucketed all-reduce overlapped with
+    backward (the default), all-reduce launched after backward (no overlap), and the all-reduce of the flat gradient
+    buffer alone."""
+    import torch
+    import torch.distributed as dist
+    from diffusion_e2e_ft_b200 import B200AutoencoderKL, B200UNet2DConditionModel, DDIMScheduler, ops
+    from diffusion_e2e_ft_b200.training import FlatTrainer, e2e_ft_loss
+    torch.manual_seed(4321)
+    with torch.device(dev):
+        unet = B200UNet2DConditionModel()
+        vae = B200AutoencoderKL()
+    vae.eval().requires_grad_(False)
+    unet.train().requires_grad_(True)
+    tr = FlatTrainer(unet, lr=3e-5, weight_decay=1e-2, max_grad_norm=1.0)
+    g = torch.Generator(device=dev).manual_seed(5 + rank)                      # different images per rank
+    rgb = torch.rand(batch, 3, res, res, device=dev, generator=g) * 2 - 1
+    gt = torch.rand(batch, 1, res, res, device=dev, generator=g) * 9.9 + 0.1
+    mask = torch.ones(batch, 1, res, res, device=dev, dtype=torch.bool)
+    ete = torch.randn(1, 77, 1024, device=dev, generator=g) * 0.5
+    sched = DDIMScheduler()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        loss, _ = e2e_ft_loss(unet, vae, sched, rgb, gt, mask, ete, modality)
+        ev[1].record()
+        tr.backward(loss)
+        ev[2].record()
+        tr.step()
+        ev[3].record()
+        return loss, ev
+
+    def timed_steps(n):
+        barrier()
+        evs, losses = [], []
+        for _ in range(n):
+            loss, ev = one_step()
+            evs.append(ev)
+            losses.append(loss)
+        barrier()
+        f = sum(e[0].elapsed_time(e[1]) for e in evs) / n
+        b = sum(e[1].elapsed_time(e[2]) for e in evs) / n
+        o = sum(e[2].elapsed_time(e[3]) for e in evs) / n
+        tot = evs[0][0].elapsed_time(evs[-1][3]) / n
+        return [f, b, o, tot], [float(l) for l in losses]
+
+    for _ in range(warmup):
+        one_step()
+    ops.STATS.reset()
+    t_on, losses = timed_steps(steps)
+    flops = sum(ops.STATS.flops.values()) / steps
+    launches = ops.STATS.launches // steps
+    t_off, ar = None, 0.0
+    if world > 1:
+        tr.overlap = False
+        one_step()
+        t_off, _ = timed_steps(steps)
+        tr.overlap = True
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record()
+        for _ in range(3):
+            dist.all_reduce(tr.flat_grad)
+        a1.record()
+        barrier()
+        ar = a0.elapsed_time(a1) / 3
+        tr.flat_grad.zero_()
+    vals = t_on + (t_off or [0.0] * 4) + [ar]
+    if world > 1:
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        vals = [float(v) for v in t]
+    f, b, o, tot = vals[:4]
+    out = {
+        "config": f"training/train.py step, SD-2 UNet (8-ch conv_in) + frozen VAE, {modality} recipe, bs={batch}/GPU "
+                  f"{res}x{res}, fp32 masters, fp16 GEMM operands, dynamic loss scale, dp{world} (BASELINE.json configs[2])",
+        "ms_per_step": tot, "samples_per_s": world * batch / (tot / 1e3), "forward_ms": f, "backward_ms": b,
+        "optimizer_ms": o, "grad_bytes": int(tr.flat_grad.numel()) * 4, "buckets": len(tr._buckets),
+        "tensor_tflops_per_gpu": flops / (tot / 1e3) / 1e12, "gpu_launches_per_step": launches,
+        "losses": losses, "finite": all(l == l and abs(l) < 1e9 for l in losses),
+        "applied_steps": tr.applied_steps(), "skipped_steps": tr.skipped_steps(), "loss_scale": tr.loss_scale(),
+        "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+    }
+    if world > 1:
+        out["allreduce"] = {
+            "collective": "NCCL all-reduce(sum) of the flat fp32 gradient, bucketed, launched from post-accumulate hooks",
+            "alone_ms": vals[8], "bus_gbs": 2 * (world - 1) / world * out["grad_bytes"] / (vals[8] / 1e3) / 1e9,
+            "step_ms_overlap_on": tot, "step_ms_overlap_off": vals[7],
+            "exposed_ms_overlap_on": max(0.0, tot - (vals[7] - vals[8])),
+            "optimizer_ms_overlap_off": vals[6]}
+    del tr, unet, vae
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(args):
+    import torch.distributed as dist
+    world, rank, local, dev = _dist_setup()
+    t = train_leg(dev, rank, world, res=args.res, batch=args.batch or 2, steps=args.steps, warmup=max(args.warmup, 2))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "train_samples_per_sec_768x768", "value": t["samples_per_s"], "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": t["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+            "config": {"workload": t["config"], "global_batch": (args.batch or 2) * world, "parallelism": f"dp{world}"},
+            "gpu_launches": t["gpu_launches_per_step"] * args.steps, "train_step": t}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from diffusion_e2e_ft_b200 import ops
+    world, rank, local, dev = _dist_setup()
+    wl = args.workload
+    bs = args.batch or {"marigold": 8, "normals": 16, "geowizard": 4}[wl]
+    res = args.res
     sdt = torch.float32 if args.stream == "fp32" else torch.float16
-    pipe = build_engine(dev, sdt, torch.float16)
+    pipe = build_engine(dev, sdt, torch.float16, wl)
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)
-    host_rgb = (torch.rand(bs, 3, res, res, generator=g) * 2 - 1).half().pin_memory()
-    host_out = torch.empty(bs, 1, res, res, dtype=torch.float16).pin_memory()
+    # the reference API hands the pipeline fp32 images (marigold_pipeline.py:245-247): fp32 pinned host buffers
+    host_rgb = (torch.rand(bs, 3, res, res, generator=g) * 2 - 1).pin_memory()
+    out_ch = {"marigold": 1, "normals": 3, "geowizard": 4}[wl]
+    host_out = torch.empty(bs, out_ch, res, res, dtype=torch.float32).pin_memory()
     dev_rgb = host_rgb.to(dev)
+    emb = (torch.randn(bs, 1, 768, device=dev) * 0.5).half() if wl == "geowizard" else None
+
+    def infer(x):
+        if wl == "geowizard":
+            d, n = pipe.single_infer(x, 1, "indoor", img_embed=emb)
+            return torch.cat([d, n], 1)
+        return pipe.single_infer(x, 1, False, noise="zeros", normals=(wl == "normals"))
 
     def step_resident():
-        return pipe.single_infer(dev_rgb, 1, False, noise="zeros")
+        return infer(dev_rgb)
 
     def step_e2e():
         x = host_rgb.to(dev, non_blocking=True)
-        y = pipe.single_infer(x, 1, False, noise="zeros")
+        y = infer(x)
         host_out.copy_(y, non_blocking=True)
         return y
 
@@ -278,7 +430,7 @@ def run_engine(args):
     clocks = sampler.stop() if sampler else None
     launches = ops.STATS.launches
     total_flops = sum(ops.STATS.flops.values())
-    flops_by_kind = dict(ops.STATS.flops)
+    flops_by_kind = {k: v / args.steps for k, v in ops.STATS.flops.items()}
 
     # ---- timed region B (roofline leg): the same step launched eagerly so every implicit-GEMM conv
     # launch can be bracketed with CUDA events on the launching stream
@@ -290,26 +442,18 @@ def run_engine(args):
     conv_ms = sum(e[0].elapsed_time(e[1]) for e in stats.events)
     conv_flops = sum(e[2] for e in stats.events)
     if args.dump_shapes and rank == 0:
-        agg = {}
-        for e in stats.lin_events:
-            a = agg.setdefault(str(e[3]), [0, 0.0, 0])
-            a[0] += 1; a[1] += e[0].elapsed_time(e[1]); a[2] += e[2]
-        rows = sorted(((k, n, ms_, fl / (ms_ / 1e3) / 1e12) for k, (n, ms_, fl) in agg.items()), key=lambda r: -r[2])
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-        with open(os.path.join(ROOT, 'gpurun_out', 'linear_shapes.txt'), 'w') as f:
-            f.write('(B,M,N,K,act,residual,out) launches total_ms TFLOP/s\n')
-            for k, n, ms_, tf in rows:
-                f.write(f'{k:55s} {n:4d} {ms_:9.3f} {tf:8.1f}\n')
-        agg = {}
-        for e in stats.events:
-            a = agg.setdefault(str(e[3]), [0, 0.0, 0])
-            a[0] += 1; a[1] += e[0].elapsed_time(e[1]); a[2] += e[2]
-        rows = sorted(((k, n, ms_, fl / (ms_ / 1e3) / 1e12) for k, (n, ms_, fl) in agg.items()), key=lambda r: -r[2])
-        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-        with open(os.path.join(ROOT, 'gpurun_out', 'conv_shapes.txt'), 'w') as f:
-            f.write('(NB,H,W,Cin,C2,Cout,taps,stride,out) launches total_ms TFLOP/s\n')
-            for k, n, ms_, tf in rows:
-                f.write(f'{k:55s} {n:4d} {ms_:9.3f} {tf:8.1f}\n')
+        for name, events in (("linear", stats.lin_events), ("conv", stats.events)):
+            agg = {}
+            for e in events:
+                a = agg.setdefault(str(e[3]), [0, 0.0, 0])
+                a[0] += 1; a[1] += e[0].elapsed_time(e[1]); a[2] += e[2]
+            rows = sorted(((k, n, ms_, fl / (ms_ / 1e3) / 1e12) for k, (n, ms_, fl) in agg.items()), key=lambda r: -r[2])
+            with open(os.path.join(ROOT, 'gpurun_out', f'{name}_shapes.txt'), 'w') as f:
+                f.write(('(B,M,N,K,act,residual,out)' if name == "linear" else '(NB,H,W,Cin,C2,Cout,taps,stride,out)')
+                        + f' launches total_ms TFLOP/s   [{rsteps} eager steps]\n')
+                for k, n, ms_, tf in rows:
+                    f.write(f'{k:55s} {n:4d} {ms_:9.3f} {tf:8.1f}\n')
     n_conv = len(stats.events)
     # per-op breakdown of one eager step (CUDA events around every op)
     ops.STATS.time_all = True
@@ -323,28 +467,49 @@ def run_engine(args):
     ops.STATS.op_events = []
     pipe.use_cuda_graph = True
 
-    # ---- UNet-only forward (part of the headline metric triple), graph-replayed
-    lat = torch.randn(bs, 8, res // 8, res // 8, device=dev, dtype=torch.float16)
-    ctx = pipe.empty_text_embed.repeat(bs, 1, 1)
-    with torch.no_grad():
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
+    # ---- UNet-only forward (part of the headline metric triple), graph-replayed: 8-channel random latent, t = 999, the
+    # batch-shared 2-token context exactly as the pipeline passes it (constant-context cross-attention, cached temb)
+    unet_ms = unet_flops = None
+    if wl != "geowizard":
+        lat = torch.randn(bs, 8, res // 8, res // 8, device=dev, dtype=torch.float16)
+        ctx = pipe.empty_text_embed.expand(bs, -1, -1)
+        with torch.no_grad():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    pipe.unet(lat, 999, encoder_hidden_states=ctx)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            ops.STATS.reset()
+            ug = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ug):
                 pipe.unet(lat, 999, encoder_hidden_states=ctx)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        ops.STATS.reset()
-        ug = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ug):
-            pipe.unet(lat, 999, encoder_hidden_states=ctx)
-        unet_flops = sum(ops.STATS.flops.values())
-        ug.replay()
-        unet_ms = timed(ug.replay, args.steps) / args.steps
+            unet_flops = sum(ops.STATS.flops.values())
+            ug.replay()
+            unet_ms = timed(ug.replay, args.steps) / args.steps
+            del ug
 
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
+
+    # ---- fast mode (fp16 residual stream, the dtype layout of the reference's own fp16 path): reported beside the
+    # default fp32-stream number, never instead of it
+    fast = None
+    if args.stream == "fp32" and not args.no_fast:
+        try:
+            del pipe._graphs
+            fpipe = build_engine(dev, torch.float16, torch.float16, wl)
+            pipe_keep, pipe = pipe, fpipe
+            for _ in range(3):
+                step_resident()
+            fms = timed(step_resident, args.steps)
+            fast = {"stream_dtype": "fp16", "value": bs * world * args.steps / (fms / 1e3), "ms_per_step": fms / args.steps}
+            pipe = pipe_keep
+            del fpipe
+        except Exception as e:  # noqa: BLE001
+            fast = {"error": repr(e)[:200]}
 
     peaks = measured_peaks()
     images = bs * world * args.steps
@@ -363,23 +528,25 @@ def run_engine(args):
             traffic_of = (f"one ncu --set full capture of {tj.get('kernel')} on {tj.get('shape')}: "
                           f"{tj.get('algorithmic_flops', 0) / 1e12:.3f} TFLOP, algorithmic bytes >= "
                           f"{tj.get('algorithmic_bytes_min', 0) / 1e9:.3f} GB ({tj.get('source')})")
+        names = {"marigold": ("marigold-e2e-ft-depth single_infer", "BASELINE.json configs[1]"),
+                 "normals": ("marigold-e2e-ft-normals single_infer", "BASELINE.json configs[4]"),
+                 "geowizard": ("geowizard-e2e-ft joint depth+normals single_infer (indoor)", "BASELINE.json configs[3]")}[wl]
         out = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if (wl == "marigold" and res == 768) else f"images_per_sec_{res}x{res}_{wl}",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": f"marigold-e2e-ft-depth single_infer bs={bs}/GPU {res}x{res}, 1 step, zeros noise "
-                                   f"(BASELINE.json configs[1])",
+            "config": {"workload": f"{names[0]} bs={bs}/GPU {res}x{res}, 1 step, zeros noise ({names[1]})",
                        "global_batch": bs * world, "parallelism": f"dp{world} (independent images, no collective)",
                        "stream_dtype": args.stream, "operands": "fp16 x fp16 -> fp32 accumulate",
                        "l2": "per-step working set (GBs of activations + 1.9 GB weights) >> 126 MB L2; no flush needed"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host_rgb.numel() * 2,
-                    "d2h_bytes_per_step": host_out.numel() * 2, "ms_per_step": e2e_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host_rgb.numel() * 4,
+                    "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": e2e_ms / args.steps,
+                    "host_dtype": "fp32 pinned"},
             "gpu_launches": launches,
-            "unet_fwd_ms": unet_ms,
-            "unet_tensor_frac": unet_flops / (unet_ms / 1e3) / 1e12 / peak,
             "step_tensor_tflops": total_flops / (ms / 1e3) / 1e12,
             "step_tensor_frac": total_flops / (ms / 1e3) / 1e12 / peak,
-            "flops_per_step": flops_by_kind,
+            "tensor_flops_per_step_by_kind": flops_by_kind,
             "breakdown_ms_eager_step": {k: round(v, 2) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1])},
             "roofline": {"kernel": "gemm_conv_kernel (implicit-GEMM conv3x3, tcgen05+TMA)", "bound": "tensor",
                          "achieved": conv_tf, "peak": peak, "unit": "TFLOP/s", "frac": conv_tf / peak,
@@ -389,7 +556,28 @@ def run_engine(args):
                          "timed_in": f"{rsteps} eagerly launched steps of the same workload ({ms_eager:.1f} ms/step eager)"},
             "clocks": clocks,
         }
-    if world > 1:
+        if unet_ms is not None:
+            out["unet_fwd_ms"] = unet_ms
+            out["unet_tensor_frac"] = unet_flops / (unet_ms / 1e3) / 1e12 / peak
+        if fast is not None:
+            out["fast_mode"] = fast
+
+    # ---- BASELINE.json configs[2]: the training step with its gradient all-reduce.  Every rank runs it in a CHILD
+    # process with its own process group (MASTER_PORT + 1): a fault or a stuck collective in the training leg can then
+    # never take the headline line down with it — the child is killed by PID after the timeout and its error recorded.
+    if wl == "marigold" and not args.no_train:
+        del pipe
+        torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        t = _train_subprocess(world, rank, local)
+        if rank == 0:
+            out["train_step"] = t
+        world_pg = False
+    else:
+        world_pg = world > 1
+    if world_pg:
         dist.barrier()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
@@ -398,8 +586,36 @@ def run_engine(args):
             except Exception as e:  # noqa: BLE001
                 out["cpu_baseline"] = {"error": repr(e)[:200]}
         print(json.dumps(out))
-    if world > 1:
+    if world_pg:
         dist.destroy_process_group()
+
+
+def _train_subprocess(world, rank, local, timeout_s=420):
+    """Run `bench.py --workload train` for this rank in a child process (own NCCL group on MASTER_PORT + 1)."""
+    env = dict(os.environ)
+    env.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(local),
+               MASTER_ADDR=env.get("MASTER_ADDR", "127.0.0.1"), MASTER_PORT=str(int(env.get("MASTER_PORT", "29500")) + 1))
+    for k in ("TORCHELASTIC_RUN_ID", "TORCHELASTIC_RESTART_COUNT", "TORCHELASTIC_MAX_RESTARTS",
+              "TORCHELASTIC_USE_AGENT_STORE", "TORCH_NCCL_ASYNC_ERROR_HANDLING"):
+        env.pop(k, None)                       # the child rendezvous is a plain env:// TCP store on the new port
+    cmd = [sys.executable, os.path.abspath(__file__), "--workload", "train", "--gpus", str(world), "--steps", "3",
+           "--warmup", "2", "--res", "768", "--batch", "2"]
+    try:
+        p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        try:
+            so, se = p.communicate(timeout=timeout_s)
+        except subprocess.TimeoutExpired:
+            p.kill()                           # exact PID of the child this rank started
+            so, se = p.communicate()
+            return {"error": f"training leg timed out after {timeout_s} s", "stderr_tail": (se or "")[-300:]}
+        if rank != 0:
+            return None
+        for line in reversed((so or "").strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line).get("train_step")
+        return {"error": f"training leg rc={p.returncode}", "stderr_tail": (se or "")[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
 
 
 def main():
@@ -408,14 +624,21 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--workload", default="marigold", choices=["marigold", "normals", "geowizard", "train"],
+                    help="marigold = configs[1] (headline); normals = configs[4] (bs 16, --res sweep); geowizard = "
+                         "configs[3] (bs 4, joint attention); train = configs[2] (bs 2/GPU training step)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--res", type=int, default=768)
     ap.add_argument("--stream", default="fp32", choices=["fp32", "fp16"], help="residual-stream dtype in the engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[2] training-step leg of the default line")
+    ap.add_argument("--no-fast", action="store_true", help="skip the fp16-stream timing of the default line")
     ap.add_argument("--dump-shapes", action="store_true", help="write per-shape conv timings to gpurun_out/")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_engine(args)
 

@@ -9,6 +9,7 @@ from .lib import load as load_library, LIB_PATH, EXPORTS  # noqa: F401
 from .unet import B200UNet2DConditionModel, UNet2DConditionOutput  # noqa: F401
 from .vae import B200AutoencoderKL  # noqa: F401
 from .pipelines import (DDIMScheduler, MarigoldPipeline, MarigoldDepthOutput,  # noqa: F401
-                        DepthNormalEstimationPipeline, DepthNormalPipelineOutput, ensemble_normals)
+                        DepthNormalEstimationPipeline, DepthNormalPipelineOutput, pyramid_noise_like)
+from .ensemble import ensemble_normals, ensemble_normals_with_index, ensemble_depths  # noqa: F401
 
 __version__ = "0.1.0"

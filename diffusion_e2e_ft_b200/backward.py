@@ -37,14 +37,15 @@ def linear_bwd(a, w, dy, need_da=True, da_dtype=F16, da_add=None, need_dw=True, 
 
 
 # -------------------------------------------------------------------------------------------------- conv
-# Experimental (round-2 work, OFF by default; host algebra verified on CPU with the kernels emulated, first hardware
-# run pending — tools/pending_gpu_checks.py):
+# Weight-gradient GEMM variants (GPU-verified in round 2: tests/test_engine_gpu.py::test_wgrad_variants; defaults chosen
+# from tools/train_step_timing.py on a B200, overridable with B200_WGRAD_PADDED / B200_WGRAD_SPLIT_K):
 #   WGRAD_PADDED  stride-1 3x3 convs: one zero-padded planar copy of X and three column-shifted copies of dY instead
 #                 of nine shifted copies of X; a kernel row (ky) is a 16-byte-aligned pointer offset of ky*Wp into X.
 #   WGRAD_SPLIT_K split the pixel contraction over `batch` so a Cout x Cin weight-gradient GEMM fills the 148 SMs;
 #                 value = target number of CTAs (0 = no split); partial sums are reduced by `col_sum`.
-WGRAD_PADDED = False
-WGRAD_SPLIT_K = 0
+import os as _os
+WGRAD_PADDED = _os.environ.get("B200_WGRAD_PADDED", "0") == "1"
+WGRAD_SPLIT_K = int(_os.environ.get("B200_WGRAD_SPLIT_K", "0"))
 WGRAD_MIN_KBLOCKS = 8        # at least this many 64-wide k-blocks per split
 
 

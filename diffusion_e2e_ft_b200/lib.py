@@ -65,7 +65,17 @@ _SIGS = {
     "b200_decode_post_bwd": (c_int, [_P, _P, c_int, _LL, c_int, _P, _P]),
     "b200_adamw_step_scaled": (c_int, [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_float, c_int, _P,
                                        c_float, c_float, _P]),
+    "b200_adamw_step_state": (c_int, [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_float, _P, c_float,
+                                      c_float, _P, c_int, c_float, c_float, c_float, _P]),
     "b200_upsample_nearest_bwd": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "b200_ensemble_normals": (c_int, [_P, c_int, _LL, _P, _P, _P, _P]),
+    "b200_ensemble_depths_objective": (c_int, [_P, _P, _P, c_int, _LL, c_int, _P, _P, _P]),
+    "b200_ensemble_depths_reduce": (c_int, [_P, _P, _P, c_int, _LL, c_int, _P, _P, _P, _P]),
+    "b200_minmax_rows": (c_int, [_P, c_int, _LL, _P, _P, _P]),
+    "b200_minmax_normalise": (c_int, [_P, _LL, _P, _P, _P]),
+    "b200_rgb_normalise": (c_int, [_P, c_int, _LL, c_int, _P, _P]),
+    "b200_resize_bilinear_aa": (c_int, [_P, _LL, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "b200_resize_nearest": (c_int, [_P, _LL, c_int, c_int, c_int, c_int, _P, _P]),
     "b200_cast_f32_to_f16": (c_int, [_P, _P, _LL, _P]),
     "b200_nhwc_to_nchw_f32": (c_int, [_P, c_int, c_int, c_int, _LL, _P, _P]),
 }

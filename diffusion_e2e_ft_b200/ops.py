@@ -462,6 +462,23 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr=3e-5, betas=(0.9, 0.99
         "b200_adamw_step_scaled")
 
 
+@_timed("optim")
+def adamw_step_state(param, grad, exp_avg, exp_avg_sq, state, grad_norm_sq_t, lr=3e-5, betas=(0.9, 0.999), eps=1e-8,
+                     weight_decay=1e-2, max_grad_norm=0.0, inv_world=1.0, dynamic_scale=True, growth_interval=2000,
+                     min_scale=1.0, max_scale=65536.0):
+    """Fused clip + AdamW driven by the device-side `state` block (fp32[8], see include/b200_e2eft.h): skipped steps
+    (non-finite / all-zero gradient) and dynamic loss scaling without a host sync."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, state, grad_norm_sq_t)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == F32 and t.is_contiguous() and t.numel() == param.numel()
+    assert state.dtype == F32 and state.numel() == 8 and state.is_contiguous()
+    _ck(_lib.load().b200_adamw_step_state(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
+                                          float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                          _p(grad_norm_sq_t), float(max_grad_norm), float(inv_world), _p(state),
+                                          int(dynamic_scale), float(growth_interval), float(min_scale), float(max_scale),
+                                          _stream()), "b200_adamw_step_state")
+
+
 @_timed("cast")
 def cast_f16(x):
     h = getattr(x, "_h16", None)

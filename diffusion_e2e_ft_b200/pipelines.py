@@ -147,30 +147,34 @@ class MarigoldDepthOutput:
     normal_colored: Optional[object]
 
 
-def ensemble_normals(input_images: torch.Tensor):
-    """marigold_pipeline.py:59-71 (host-side torch; the argmin index selection is bit-exact by
-    construction: same ops, same order)."""
-    normal_preds = input_images
-    bsz, d, h, w = normal_preds.shape
-    normal_preds = normal_preds / (torch.norm(normal_preds, p=2, dim=1).unsqueeze(1) + 1e-5)
-    phi = torch.atan2(normal_preds[:, 1, :, :], normal_preds[:, 0, :, :]).mean(dim=0)
-    theta = torch.atan2(torch.norm(normal_preds[:, :2, :, :], p=2, dim=1), normal_preds[:, 2, :, :]).mean(dim=0)
-    normal_pred = torch.zeros((d, h, w)).to(normal_preds)
-    normal_pred[0, :, :] = torch.sin(theta) * torch.cos(phi)
-    normal_pred[1, :, :] = torch.sin(theta) * torch.sin(phi)
-    normal_pred[2, :, :] = torch.cos(theta)
-    angle_error = torch.acos(torch.clip(torch.cosine_similarity(normal_pred[None], normal_preds, dim=1), -0.999, 0.999))
-    normal_idx = torch.argmin(angle_error.reshape(bsz, -1).sum(-1))
-    return normal_preds[normal_idx], None
+from .ensemble import (ensemble_depths, ensemble_normals, minmax_normalise_, minmax_rows, normalise_rgb,  # noqa: E402
+                       resize_bilinear_aa, resize_nearest)
 
 
-def _resize_max_res(img, max_edge, mode="bilinear"):
-    """Marigold/marigold/util/image_util.py resize_max_res (antialiased downscale to max edge)."""
+def pyramid_noise_like(x, discount=0.9, generator=None):
+    """Multi-resolution noise of marigold_pipeline.py:76-86 (also training/train.py:486-487): white noise plus
+    bilinearly up-sampled coarser noise maps with geometrically decaying weights, renormalised to unit std.  The
+    random draws (torch.randn, python `random`) are host-pipeline code as in the reference; they are not part of
+    the measured hot path (E2E-FT uses zeros noise)."""
+    import random
+    b, c, w, h = x.shape
+    u = torch.nn.Upsample(size=(w, h), mode="bilinear")
+    noise = torch.randn(x.shape, device=x.device, dtype=x.dtype, generator=generator)
+    for i in range(10):
+        r = random.random() * 2 + 2
+        w, h = max(1, int(w / (r ** i))), max(1, int(h / (r ** i)))
+        noise += u(torch.randn(b, c, w, h, device=x.device, dtype=x.dtype, generator=generator)) * discount ** i
+        if w == 1 or h == 1:
+            break
+    return noise / noise.std()
+
+
+def _resize_max_res(img, max_edge):
+    """Marigold/marigold/util/image_util.py:79-108 resize_max_res: antialiased bilinear down-scale to a maximum edge
+    length, on the device (csrc/postproc.cu)."""
     _, h, w = img.shape
     s = min(max_edge / w, max_edge / h)
-    nh, nw = int(h * s), int(w * s)
-    return torch.nn.functional.interpolate(img[None].float(), size=(nh, nw), mode=mode, antialias=True,
-                                           align_corners=False)[0]
+    return resize_bilinear_aa(img, (int(h * s), int(w * s)))
 
 
 class MarigoldPipeline(PipelineBase):
@@ -188,16 +192,25 @@ class MarigoldPipeline(PipelineBase):
                  batch_size: int = 0, color_map: Optional[str] = "Spectral", show_progress_bar: bool = True,
                  ensemble_kwargs=None, noise="gaussian", normals=False) -> MarigoldDepthOutput:
         assert processing_res >= 0 and ensemble_size >= 1
+        if resample_method != "bilinear":
+            raise NotImplementedError("the engine resizes with the reference's default (bilinear, antialiased)")
         if isinstance(input_image, torch.Tensor):
             rgb = input_image.squeeze()
         else:                                              # PIL.Image
             rgb = torch.from_numpy(np.asarray(input_image.convert("RGB")).copy()).permute(2, 0, 1)
         input_size = rgb.shape
         assert rgb.dim() == 3 and input_size[0] == 3, f"Wrong input shape {input_size}, expected [rgb, H, W]"
+        # pre-processing on the device: the raw (uint8) image is uploaded once; resize + [0,255] ->
+        # [-1,1] run as kernels (marigold_pipeline.py:237-247)
+        was_u8 = rgb.dtype == torch.uint8
+        rgb = rgb.to(self.device)
+        rgb = rgb.to(torch.float32)                        # dtype cast at the API boundary
         if processing_res > 0:
-            rgb = _resize_max_res(rgb, processing_res, resample_method)
-        rgb_norm = (rgb / 255.0 * 2.0 - 1.0).to(self.dtype)
-        assert rgb_norm.min() >= -1.0 and rgb_norm.max() <= 1.0
+            rgb = _resize_max_res(rgb, processing_res)
+        rgb_norm = normalise_rgb(rgb, round_u8=was_u8 and processing_res > 0)
+        lo, hi = minmax_rows(rgb_norm.view(1, -1))[0].tolist()
+        assert lo >= -1.0 and hi <= 1.0
+        rgb_norm = rgb_norm.to(self.dtype)
         duplicated = torch.stack([rgb_norm] * ensemble_size)
         bs = batch_size if batch_size > 0 else ensemble_size
         preds = []
@@ -206,22 +219,27 @@ class MarigoldPipeline(PipelineBase):
                                            noise=noise, normals=normals).detach())
         preds = torch.concat(preds, dim=0).squeeze()
         pred_uncert = None
-        if ensemble_size > 1:
-            if not normals:
-                raise NotImplementedError("depth ensembling (scipy BFGS) is outside the engine; use ensemble_size=1")
-            pred, pred_uncert = ensemble_normals(preds)
+        if ensemble_size > 1:                              # test-time ensembling on the device (:288-294)
+            if normals:
+                pred, pred_uncert = ensemble_normals(preds)
+            else:
+                pred, pred_uncert = ensemble_depths(preds, **(ensemble_kwargs or {}))
         else:
             pred = preds
+        pred = pred.to(torch.float32).contiguous()
         if normals:
-            pred = pred / (torch.norm(pred, p=2, dim=0, keepdim=True) + 1e-5)
+            pred = ops.decode_post(pred[None], normals=True)[0]            # pred / (|pred| + 1e-5)   (:300-303)
         else:
-            min_d, max_d = torch.min(pred), torch.max(pred)
-            pred = torch.zeros_like(pred) if max_d == min_d else (pred - min_d) / (max_d - min_d)
+            pred, mm = minmax_normalise_(pred)                             # (pred - min) / (max - min)   (:305-312)
+            lo, hi = mm.tolist()
+            if hi == lo:
+                pred = torch.zeros_like(pred)
         if match_input_res:
-            p4 = (pred if normals else pred.unsqueeze(0))[None].float()
-            pred = torch.nn.functional.interpolate(p4, size=(input_size[-2], input_size[-1]), mode=resample_method,
-                                                   antialias=True, align_corners=False)[0].squeeze()
+            pred = resize_bilinear_aa(pred if normals else pred.unsqueeze(0),
+                                      (input_size[-2], input_size[-1])).squeeze()
         pred = pred.cpu().numpy()
+        if pred_uncert is not None:
+            pred_uncert = pred_uncert.cpu().numpy() if torch.is_tensor(pred_uncert) else pred_uncert
         pred = pred.clip(-1.0, 1.0) if normals else pred.clip(0, 1)
         # colourising needs matplotlib (absent): the color_map=None path of marigold_pipeline.py:330-338
         return MarigoldDepthOutput(depth_np=None if normals else pred, depth_colored=None, uncertainty=pred_uncert,
@@ -259,6 +277,8 @@ class MarigoldPipeline(PipelineBase):
         rgb_latent = self.encode_rgb(rgb_in)
         if noise == "gaussian":
             latent = torch.randn(rgb_latent.shape, device=device, dtype=rgb_latent.dtype, generator=generator)
+        elif noise == "pyramid":
+            latent = pyramid_noise_like(rgb_latent, generator=generator)
         elif noise == "zeros":
             latent = None                                   # exact zeros: never materialised
         else:
@@ -392,23 +412,32 @@ class DepthNormalEstimationPipeline(PipelineBase):
     def __call__(self, input_image, denoising_steps: int = 1, ensemble_size: int = 1, processing_res: int = 768,
                  match_input_res: bool = True, domain: str = "indoor", color_map: Optional[str] = None,
                  show_progress_bar: bool = False, noise="zeros", img_embed=None) -> DepthNormalPipelineOutput:
-        assert ensemble_size == 1, "E2E-FT setting: ensemble_size=1 (geowizard_pipeline.py:136)"
         if isinstance(input_image, torch.Tensor):
             rgb = input_image.squeeze()
         else:
             rgb = torch.from_numpy(np.asarray(input_image.convert("RGB")).copy()).permute(2, 0, 1)
         input_size = rgb.shape
+        was_u8 = rgb.dtype == torch.uint8
+        rgb = rgb.to(self.device).to(torch.float32)
         if processing_res > 0:
             rgb = _resize_max_res(rgb, processing_res)
-        rgb_norm = (rgb / 255.0 * 2.0 - 1.0).to(self.dtype)[None].to(self.device)
-        depth, normal = self.single_infer(rgb_norm, denoising_steps, domain, show_progress_bar, noise, img_embed)
-        depth, normal = depth.squeeze(), normal.squeeze()
-        min_d, max_d = torch.min(depth), torch.max(depth)
-        depth = (depth - min_d) / (max_d - min_d)
+        rgb_norm = normalise_rgb(rgb, round_u8=was_u8 and processing_res > 0).to(self.dtype)
+        dl, nl = [], []
+        for _ in range(ensemble_size):                      # geowizard_pipeline.py:139-176 (batch size 1 per member)
+            d, n = self.single_infer(rgb_norm[None], denoising_steps, domain, show_progress_bar, noise, img_embed)
+            dl.append(d)
+            nl.append(n)
+        depth, normal = torch.cat(dl).squeeze(), torch.cat(nl).squeeze()
+        uncert = None
+        if ensemble_size > 1:                               # :179-188
+            depth, uncert = ensemble_depths(depth)
+            normal, _ = ensemble_normals(normal)
+        depth, _ = minmax_normalise_(depth.to(torch.float32).contiguous())      # :192-194
+        normal = normal.to(torch.float32)
         if match_input_res:
-            depth = torch.nn.functional.interpolate(depth[None, None].float(), size=tuple(input_size[-2:]),
-                                                    mode="bilinear", antialias=True)[0, 0]
-            normal = torch.nn.functional.interpolate(normal[None].float(), size=tuple(input_size[-2:]),
-                                                     mode="nearest")[0]
+            # the reference resizes on the host (PIL for depth, cv2 INTER_NEAREST for normals, :201-206); here on the device
+            depth = resize_bilinear_aa(depth[None], tuple(input_size[-2:]))[0]
+            normal = resize_nearest(normal, tuple(input_size[-2:]))
         return DepthNormalPipelineOutput(depth_np=depth.cpu().numpy().clip(0, 1), depth_colored=None,
-                                         normal_np=normal.cpu().numpy().clip(-1, 1), normal_colored=None)
+                                         normal_np=normal.cpu().numpy().clip(-1, 1), normal_colored=None,
+                                         uncertainty=None if uncert is None else uncert.cpu().numpy())

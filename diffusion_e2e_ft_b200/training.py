@@ -95,24 +95,39 @@ class FlatTrainer:
     and their gradients are re-homed as views of two flat fp32 buffers, so `backward()` accumulates straight into
     the buffer the gradient all-reduce and the fused clip + AdamW kernel work on.
 
-        tr = FlatTrainer(unet, lr=3e-5)
-        loss, _ = e2e_ft_loss(unet, vae, scheduler, rgb, gt, mask, empty_encoding, "depth")
-        tr.backward(loss)            # (loss * LOSS_SCALE / accumulation_steps).backward()
-        tr.step()                    # all-reduce, clip, AdamW, zero the gradient buffer
+        tr = FlatTrainer(unet, lr=3e-5, accumulation_steps=16)
+        for batch in loader:                                      # one micro-batch per iteration
+            loss, _ = e2e_ft_loss(unet, vae, scheduler, rgb, gt, mask, empty_encoding, "depth")
+            tr.micro_step(loss)      # backward; on every `accumulation_steps`-th call also all-reduce + clip + AdamW
 
-    Data parallel (one process per GPU, `torch.distributed` initialised): the flat gradient is cut into buckets of
-    `bucket_mb`; a bucket's SUM all-reduce is launched asynchronously (NCCL stream) the moment autograd has
-    accumulated its last parameter, i.e. it overlaps the rest of the backward pass — the reference gets the same
-    from accelerate's DDP (train.py:470).  The 1/world_size of the average is folded into the optimizer kernel's
-    unscale factor, so no extra pass over the 3.46 GB buffer.  `backward(loss, sync=False)` skips the exchange on
-    the non-final micro-steps of a gradient accumulation (DDP `no_sync`)."""
+    (`tr.backward(loss); tr.step()` is the same thing spelled out for accumulation_steps == 1.)
+
+    Gradient accumulation (`accelerator.accumulate`, train.py:470): micro-steps are counted here; only the LAST backward
+    of an accumulation window exchanges gradients (DDP `no_sync` on the others), and `step()` refuses to run in the
+    middle of a window.  Data parallel (one process per GPU, `torch.distributed` initialised): the flat gradient is cut
+    into buckets of `bucket_mb` in gradient-ready order — the parameters whose gradients only arrive at the very end
+    of backward (every resnet's `time_emb_proj` and the time / class embedding MLPs, produced by the embedding block
+    that runs first in forward) get their own bucket, so they do not hold the others back; a bucket's SUM all-reduce is
+    launched asynchronously (NCCL stream) the moment autograd has accumulated its last parameter, i.e. it overlaps the
+    rest of the backward pass as accelerate's DDP does for the reference.  The 1/world_size of the average is folded
+    into the optimizer kernel's gradient multiplier (no extra pass over the 3.46 GB buffer).
+
+    Mixed precision: backward GEMM operands are fp16, so the loss is multiplied by a loss scale held ON THE DEVICE
+    (`state[0]`); the fused optimizer kernel skips the step and halves the scale when the gradient norm is non-finite,
+    doubles it after `growth_interval` good steps, and also skips when the gradient is exactly zero (all masks empty:
+    train.py:503,546-551) — all without a host sync.  `skipped_steps()` / `loss_scale()` read the state back."""
+
+    LATE_GRAD_KEYS = ("time_emb_proj", "time_embedding", "class_embedding")
 
     def __init__(self, module, lr=3e-5, weight_decay=1e-2, max_grad_norm=1.0, accumulation_steps=1, group=None,
-                 loss_scale=LOSS_SCALE, bucket_mb=256):
+                 loss_scale=LOSS_SCALE, bucket_mb=256, dynamic_loss_scale=True, growth_interval=2000, overlap=True):
         import torch.distributed as dist
-        ps = [p for p in module.parameters() if p.requires_grad]
-        if not ps:
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if not named:
             raise ValueError("no trainable parameters")
+        late = [(n, p) for n, p in named if any(k in n for k in self.LATE_GRAD_KEYS)]
+        rest = [(n, p) for n, p in named if not any(k in n for k in self.LATE_GRAD_KEYS)]
+        ps = [p for _, p in late] + [p for _, p in rest]          # flat order == reverse gradient-ready order
         dev = ps[0].device
         sizes = [(p.numel() + 3) // 4 * 4 for p in ps]                     # keep every view 16-byte aligned
         total = sum(sizes)
@@ -120,8 +135,9 @@ class FlatTrainer:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.state = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.state[0] = float(loss_scale)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        # buckets: contiguous ranges of the flat buffer in parameter order (backward fills them back to front)
         cap = max(1, int(bucket_mb * 2 ** 20 / 4))
         self._buckets, self._bucket_of = [], {}
         off = start = count = 0
@@ -136,20 +152,21 @@ class FlatTrainer:
                 self._bucket_of[id(p)] = len(self._buckets)
                 off += n
                 count += 1
-                if off - start >= cap or idx == len(ps) - 1:
+                if off - start >= cap or idx == len(ps) - 1 or idx == len(late) - 1:
                     self._buckets.append(dict(lo=start, hi=off, n=count))
                     start, count = off, 0
         self.params, self.step_count = ps, 0
         self.lr, self.weight_decay, self.max_grad_norm = lr, weight_decay, max_grad_norm
-        self.accumulation_steps, self.group, self.loss_scale = accumulation_steps, group, loss_scale
-        self._sync, self._ready, self._handles = True, [0] * len(self._buckets), {}
+        self.accumulation_steps, self.group = max(1, int(accumulation_steps)), group
+        self.dynamic_loss_scale, self.growth_interval, self.overlap = dynamic_loss_scale, growth_interval, overlap
+        self._sync, self._ready, self._handles, self._micro, self._synced = True, [0] * len(self._buckets), {}, 0, True
         if self.world > 1:
             for p in ps:
                 p.register_post_accumulate_grad_hook(self._on_grad)
 
     # autograd calls this right after it has added a parameter's gradient into its view of the flat buffer
     def _on_grad(self, p):
-        if not self._sync:
+        if not (self._sync and self.overlap):
             return
         b = self._bucket_of[id(p)]
         self._ready[b] += 1
@@ -162,27 +179,56 @@ class FlatTrainer:
         self._handles[b] = dist.all_reduce(self.flat_grad[bk["lo"]:bk["hi"]], op=dist.ReduceOp.SUM, group=self.group,
                                            async_op=True)
 
-    def backward(self, loss, sync=True):
-        self._sync = sync
+    def backward(self, loss, sync=None):
+        """(loss * loss_scale / accumulation_steps).backward().  `sync=None`: exchange gradients only on the last
+        micro-step of the accumulation window (counted here); an explicit True / False overrides."""
+        last = (self._micro + 1) % self.accumulation_steps == 0
+        sync = last if sync is None else bool(sync)
+        if self._handles:
+            raise RuntimeError("FlatTrainer.backward: gradient all-reduces of the previous backward are still in flight "
+                               "— call step() first (or backward(..., sync=False) on non-final micro-steps)")
+        self._sync, self._synced = sync, sync
         self._ready = [0] * len(self._buckets)
-        (loss * (self.loss_scale / self.accumulation_steps)).backward()
+        self._micro += 1
+        (loss * (self.state[0] / self.accumulation_steps)).backward()
+
+    def micro_step(self, loss, lr=None):
+        """backward(); on the last micro-step of the accumulation window also step().  Returns True when it stepped
+        (`accelerator.sync_gradients` of train.py:563-570)."""
+        self.backward(loss)
+        if self._micro % self.accumulation_steps == 0:
+            self.step(lr)
+            return True
+        return False
 
     def step(self, lr=None):
+        if self._micro % self.accumulation_steps != 0 or not self._synced:
+            raise RuntimeError(f"FlatTrainer.step inside an accumulation window ({self._micro % self.accumulation_steps} of "
+                               f"{self.accumulation_steps} micro-steps) or after backward(sync=False): gradients are not reduced")
         self.step_count += 1
-        unscale = 1.0 / self.loss_scale
         if self.world > 1:
-            for b in range(len(self._buckets)):                    # parameters without a gradient this step
+            for b in range(len(self._buckets)):                    # parameters without a gradient this step / overlap off
                 if b not in self._handles:
                     self._launch(b)
             for h in self._handles.values():
                 h.wait()
             self._handles = {}
-            unscale /= self.world                                  # SUM -> mean, folded into the optimizer kernel
         from .modules import bump_weights_epoch
         nsq = ops.grad_norm_sq(self.flat_grad)
-        ops.adamw_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
-                       lr=self.lr if lr is None else lr, weight_decay=self.weight_decay, grad_norm_sq_t=nsq,
-                       max_grad_norm=self.max_grad_norm, grad_unscale=unscale)
+        ops.adamw_step_state(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.state, nsq,
+                             lr=self.lr if lr is None else lr, weight_decay=self.weight_decay,
+                             max_grad_norm=self.max_grad_norm, inv_world=1.0 / self.world,
+                             dynamic_scale=self.dynamic_loss_scale, growth_interval=self.growth_interval)
         bump_weights_epoch()
         self.flat_grad.zero_()
         return nsq
+
+    # ---- host read-backs (each one is a device sync: for logging / tests, not for the training loop)
+    def loss_scale(self):
+        return float(self.state[0])
+
+    def applied_steps(self):
+        return int(self.state[2])
+
+    def skipped_steps(self):
+        return int(self.state[3])

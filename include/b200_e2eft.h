@@ -186,6 +186,17 @@ int b200_adamw_step_scaled(float* param, const float* grad, float* exp_avg, floa
                            float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                            const double* grad_norm_sq, float max_grad_norm, float grad_unscale, void* stream);
 
+/* Same update driven by a device-side state block (fp32[8]: loss scale, growth tracker, applied steps, skipped
+ * steps, skipped flag, gradient multiplier, bc1, bc2) so that neither the skip decision nor dynamic loss scaling
+ * needs a host sync: the step is skipped (parameters and moments untouched, as torch.optim.AdamW leaves parameters
+ * whose .grad is None) when the gradient norm is non-finite (fp16 overflow of the loss-scaled backward: the scale is
+ * halved) or exactly zero (empty validity masks / NaN loss: training/train.py:503,546-551 back-propagates 0).
+ * `grad` holds (loss scale x world size) x the mean gradient; inv_world = 1 / data-parallel ranks. */
+int b200_adamw_step_state(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                          float lr, float beta1, float beta2, float eps, float weight_decay,
+                          const double* grad_norm_sq, float max_grad_norm, float inv_world, float* state,
+                          int dynamic_scale, float growth_interval, float min_scale, float max_scale, void* stream);
+
 /* ---- Backward pass (training/train.py:545-566, `accelerator.backward(loss)`).  The GEMM-shaped halves run on
  * b200_linear / b200_conv2d_nhwc with re-packed operands; these are the streaming / reduction kernels around them.
  *
@@ -247,6 +258,33 @@ void b200_debug_force_block_n(int bn);
 void b200_debug_set_flags(int flags);
 /* 1 (default) = swap operands automatically when Cout % 128 == 0; 0 = never */
 void b200_debug_set_swap(int mode);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host-pipeline post/pre-processing on the device.
+ *
+ * b200_ensemble_normals: Marigold/marigold/marigold_pipeline.py:59-71 == GeoWizard/geowizard/utils/
+ *   normal_ensemble.py:6-22.  preds [E][3][HW] fp32 (E <= 32) -> out [3][HW] = preds[index] / (|.| + 1e-5) with
+ *   index = argmin_e sum_pixels acos(clip(cos(mean-angle normal, n_e), +-0.999)); err_ws = double[E] scratch.
+ * b200_ensemble_depths_objective / _reduce: Marigold/marigold/util/ensemble.py:40-132.  imgs [E][HW] fp32, s/t [E]
+ *   device fp32.  objective: ws (double[2] scratch) [0] = sum over pixels and pairs i<j of (v_i - v_j)^2,
+ *   out3[1], out3[2] = min / max of the reduced map (the scipy-BFGS closure :74-98 finishes on the host);
+ *   reduce: aligned / uncertainty [HW] = median + MAD (reduction 0) or mean + std (1), scaled to [0, 1] (:110-130).
+ * b200_minmax_rows: per-row (min, max) of [rows][cols] fp32 -> out[rows][2] (ws: uint32[2*rows]) (:66-69 init guess).
+ * b200_minmax_normalise: x = (x - min x) / (max x - min x) in place (marigold_pipeline.py:305-312); minmax_out[2] opt.
+ * b200_rgb_normalise: uint8 / fp32 [0,255] -> fp32 x / 255 * 2 - 1 (:245-247).
+ * b200_resize_bilinear_aa: torchvision resize(..., BILINEAR, antialias=True) of [planes][H][W] fp32 (:237-242,315-321),
+ *   separable (width then height), tmp = [planes][H][OW] scratch.   b200_resize_nearest: geowizard normals. */
+int b200_ensemble_normals(const float* preds, int E, long long HW, double* err_ws, float* out, int* index, void* stream);
+int b200_ensemble_depths_objective(const float* imgs, const float* s, const float* t, int E, long long HW,
+                                   int reduction, double* ws, float* out3, void* stream);
+int b200_ensemble_depths_reduce(const float* imgs, const float* s, const float* t, int E, long long HW, int reduction,
+                                double* ws, float* aligned, float* uncertainty, void* stream);
+int b200_minmax_rows(const float* x, int rows, long long cols, unsigned int* ws, float* out, void* stream);
+int b200_minmax_normalise(float* x, long long n, unsigned int* ws, float* minmax_out, void* stream);
+int b200_rgb_normalise(const void* x, int in_u8, long long n, int round_u8, float* out, void* stream);
+int b200_resize_bilinear_aa(const float* x, long long planes, int H, int W, int OH, int OW, float* tmp, float* out,
+                            void* stream);
+int b200_resize_nearest(const float* x, long long planes, int H, int W, int OH, int OW, float* out, void* stream);
 
 #ifdef __cplusplus
 }

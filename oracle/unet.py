@@ -400,5 +400,8 @@ def replace_unet_conv_in(unet: UNet2DConditionRef, repeat: int = 2):
     new.weight = nn.Parameter(w)
     new.bias = nn.Parameter(b)
     unet.conv_in = new
-    unet.config.in_channels = w.shape[1]
+    if isinstance(unet.config, dict):                     # unet_prep.py:20 writes unet.config['in_channels']
+        unet.config["in_channels"] = w.shape[1]
+    else:                                                 # the oracle's own config is a dataclass
+        unet.config.in_channels = w.shape[1]
     return unet

@@ -355,6 +355,31 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr=3e-5, betas=(0.9, 0.99
     param.addcdiv_(exp_avg, exp_avg_sq.sqrt() / math.sqrt(bc2) + eps, value=-lr / bc1)
 
 
+def adamw_step_state(param, grad, exp_avg, exp_avg_sq, state, grad_norm_sq_t, lr=3e-5, betas=(0.9, 0.999), eps=1e-8,
+                     weight_decay=1e-2, max_grad_norm=0.0, inv_world=1.0, dynamic_scale=True, growth_interval=2000,
+                     min_scale=1.0, max_scale=65536.0):
+    """include/b200_e2eft.h b200_adamw_step_state: state = [scale, tracker, applied, skipped, skip flag, mult, bc1, bc2]."""
+    nsq = float(grad_norm_sq_t)
+    S = float(state[0])
+    unscale = inv_world / S
+    if not math.isfinite(nsq) or nsq == 0.0:
+        state[3] += 1
+        state[4] = 1
+        if not math.isfinite(nsq) and dynamic_scale:
+            state[0] = max(S * 0.5, min_scale)
+            state[1] = 0
+        return
+    state[2] += 1
+    state[4] = 0
+    step = int(state[2])
+    adamw_step(param, grad, exp_avg, exp_avg_sq, step, lr, betas, eps, weight_decay, grad_norm_sq_t, max_grad_norm, unscale)
+    if dynamic_scale:
+        state[1] += 1
+        if float(state[1]) >= growth_interval:
+            state[0] = min(S * 2.0, max_scale)
+            state[1] = 0
+
+
 def _nearest_index(n_in, n_out):
     return torch.clamp((torch.arange(n_out) * n_in) // n_out, max=n_in - 1)
 
@@ -382,7 +407,7 @@ _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm
                  softmax_groups=softmax_groups, cast_f16=cast_f16, im2col3x3=im2col3x3, conv3x3_small_cout=conv3x3_small_cout,
                  timestep_embedding=timestep_embedding, nhwc_to_nchw_f32=nhwc_to_nchw_f32,
                  pointwise_nchw=pointwise_nchw, decode_post=decode_post, ssi_loss=ssi_loss, angular_loss=angular_loss,
-                 ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd, grad_norm_sq=grad_norm_sq, adamw_step=adamw_step,
+                 ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd, grad_norm_sq=grad_norm_sq, adamw_step=adamw_step, adamw_step_state=adamw_step_state,
                  upsample_nearest=upsample_nearest, upsample_nearest_bwd=upsample_nearest_bwd)
 
 

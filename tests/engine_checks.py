@@ -340,3 +340,35 @@ def run_training_loop_tiny(device="cuda:0", steps=3, lr=1e-4):
         ne += de.pow(2).sum().item()
         no += do.pow(2).sum().item()
     return dict(loss_engine=le, loss_oracle=lo, update_cosine=dot / (ne * no) ** 0.5, update_norm_ratio=(ne / no) ** 0.5)
+
+
+def run_checkpointing_tiny(device="cuda:0"):
+    """Gradients with and without unet.enable_gradient_checkpointing() on the same weights / inputs, plus the
+    checkpointed run against the oracle's autograd."""
+    unet_ref, _ = MG.build_tiny()
+    unet_ref.requires_grad_(True)
+    x, c, dy = MG.inputs(1, 2, 8, 16, 16), MG.inputs(2, 2, 77, 128, scale=0.5), MG.inputs(7, 2, 4, 16, 16)
+    (unet_ref(x, 999, c).sample * dy).sum().backward()
+    grads = []
+    for ck in (False, True):
+        unet, _ = engine_from_oracle(unet_ref, None, device)
+        unet.requires_grad_(True)
+        if ck:
+            unet.enable_gradient_checkpointing()
+        y = unet(x.to(device), 999, c.to(device)).sample
+        (y * dy.to(device)).sum().backward()
+        grads.append({n: p.grad.detach().float().cpu() for n, p in unet.named_parameters()})
+    num = den = num_o = den_o = 0.0
+    worst, worst_name = 0.0, None
+    ref = dict(unet_ref.named_parameters())
+    for n in grads[0]:
+        a, b = grads[0][n], grads[1][n]
+        e = rel_l2(b, a)
+        if e > worst:
+            worst, worst_name = e, n
+        num += (a - b).pow(2).sum().item()
+        den += a.pow(2).sum().item()
+        num_o += (b - ref[n].grad).pow(2).sum().item()
+        den_o += ref[n].grad.pow(2).sum().item()
+    return dict(global_rel_diff=(num / den) ** 0.5, worst_rel_diff=worst, worst_name=worst_name,
+                ckpt_vs_oracle_global=(num_o / den_o) ** 0.5)

@@ -328,6 +328,54 @@ def check_adamw(seed=61, n=100003):
     return worst, 2e-6
 
 
+def check_adamw_state(seed=67, n=100003):
+    """State-driven fused clip + AdamW (device-side skip decision + dynamic loss scale, no host sync) vs
+    torch.optim.AdamW + clip_grad_norm_: three good steps with a loss-scaled, world-summed gradient buffer, then a
+    non-finite gradient (step skipped, scale halved), an all-zero gradient (skipped, scale kept), another good step
+    (bias correction continues from the APPLIED step count), and scale growth after `growth_interval` good steps."""
+    p0 = _rand(n, seed=seed, dtype=torch.float32)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=3e-3, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    state = torch.zeros(8, dtype=torch.float32, device=DEV)
+    state[0] = 1024.0
+    world = 4
+    worst = 0.0
+
+    def engine_step(g_true):
+        S = float(state[0])
+        g = g_true * (S * world)
+        nsq = ops.grad_norm_sq(g)
+        ops.adamw_step_state(p, g, m, v, state, nsq, lr=3e-3, max_grad_norm=1.0, inv_world=1.0 / world,
+                             dynamic_scale=True, growth_interval=3)
+        torch.cuda.synchronize()
+
+    def ref_step(g_true):
+        ref_p.grad = g_true.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+
+    for step in range(1, 3):
+        g = _rand(n, seed=seed + step, dtype=torch.float32) * (3.0 if step == 2 else 0.001)
+        ref_step(g); engine_step(g)
+        worst = max(worst, rel_l2(p, ref_p.data))
+    assert state.tolist()[:5] == [1024.0, 2.0, 2.0, 0.0, 0.0], state.tolist()
+    keep = (p.clone(), m.clone(), v.clone())
+    bad = _rand(n, seed=seed + 9, dtype=torch.float32)
+    bad[5] = float("inf")
+    engine_step(bad)                                                   # overflow: skipped, scale halves, tracker resets
+    assert all(torch.equal(a, b) for a, b in zip(keep, (p, m, v))) and state.tolist()[:5] == [512.0, 0.0, 2.0, 1.0, 1.0]
+    engine_step(torch.zeros(n, device=DEV))                            # empty masks: skipped, scale kept
+    assert all(torch.equal(a, b) for a, b in zip(keep, (p, m, v))) and state.tolist()[:5] == [512.0, 0.0, 2.0, 2.0, 1.0]
+    for step in range(3, 6):                                           # 3 good steps -> scale doubles once
+        g = _rand(n, seed=seed + step, dtype=torch.float32) * 0.01
+        ref_step(g); engine_step(g)
+        worst = max(worst, rel_l2(p, ref_p.data))
+    assert state.tolist()[:5] == [1024.0, 0.0, 5.0, 2.0, 0.0], state.tolist()
+    return worst, 2e-6
+
+
 def check_upsample(in_f32=False, out_hw=None):
     dt = torch.float32 if in_f32 else torch.float16
     x = _rand(2, 7, 9, 64, dtype=dt)
@@ -509,6 +557,7 @@ CHECKS = {
     "pointwise_post": check_pointwise_and_post,
     "losses_ssi_angular": check_losses,
     "adamw_clip_fused": check_adamw,
+    "adamw_state_skip_dynamic_scale": check_adamw_state,
 }
 
 

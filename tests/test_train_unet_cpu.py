@@ -68,34 +68,61 @@ dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29587", rank=r, wor
 unet_ref, vae_ref = MG.build_tiny()
 unet, vae = E.engine_from_oracle(unet_ref, vae_ref, "cpu")
 unet.requires_grad_(True)
-tr = FlatTrainer(unet, lr=1e-4, bucket_mb=0.25)               # many buckets: async all-reduce per bucket
+tr = FlatTrainer(unet, lr=1e-4, bucket_mb=0.25, accumulation_steps=2)   # many buckets: async all-reduce per bucket
 assert len(tr._buckets) > 4
+late = sum((p.numel() + 3) // 4 * 4 for n, p in unet.named_parameters() if any(k in n for k in tr.LATE_GRAD_KEYS))
+assert any(b["hi"] == late for b in tr._buckets)        # late-gradient parameters lead the flat order, own bucket(s)
 g = torch.Generator().manual_seed(100 + r)                     # different images on each rank
-rgb = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
-gt = torch.rand(1, 1, 64, 64, generator=g) * 9.9 + 0.1
-mask = torch.rand(1, 1, 64, 64, generator=g) > 0.2
 ctx = MG.inputs(5, 1, 77, 128, scale=0.5)
-loss, _ = e2e_ft_loss(unet, vae, DDIMScheduler(), rgb, gt, mask, ctx, "depth")
+def batch():
+    return (torch.rand(1, 3, 64, 64, generator=g) * 2 - 1, torch.rand(1, 1, 64, 64, generator=g) * 9.9 + 0.1,
+            torch.rand(1, 1, 64, 64, generator=g) > 0.2)
+micro = [batch(), batch()]                                     # one accumulation window = two micro-batches per rank
 before = tr.flat_param.clone()
-# the local (pre-exchange) gradient: same micro-step without the exchange, on a scratch copy of the buffer
-tr.backward(loss, sync=False)
-local = tr.flat_grad.clone()
-tr.flat_grad.zero_()
-loss, _ = e2e_ft_loss(unet, vae, DDIMScheduler(), rgb, gt, mask, ctx, "depth")
-tr.backward(loss)                                             # buckets all-reduce while backward is still running
-tr.step()
+# the local (pre-exchange) gradients of both micro-steps, on a scratch pass without the exchange
+local = []
+for rgb, gt, mask in micro:
+    loss, _ = e2e_ft_loss(unet, vae, DDIMScheduler(), rgb, gt, mask, ctx, "depth")
+    tr.backward(loss, sync=False)
+    local.append(tr.flat_grad.clone())
+    tr.flat_grad.zero_()
+tr._micro = 0
+# the real window: micro-step 1 accumulates locally (no exchange), micro-step 2 all-reduces bucket by bucket while
+# backward is still running, then clip + AdamW
+stepped = []
+for rgb, gt, mask in micro:
+    loss, _ = e2e_ft_loss(unet, vae, DDIMScheduler(), rgb, gt, mask, ctx, "depth")
+    if not stepped:
+        try:
+            tr.step()
+            raise SystemExit("step() inside an accumulation window must raise")
+        except RuntimeError:
+            pass
+    stepped.append(tr.micro_step(loss))
+assert stepped == [False, True], stepped
 both = [torch.zeros_like(tr.flat_param) for _ in range(2)]
 dist.all_gather(both, tr.flat_param)
 assert torch.equal(both[0], both[1]), "ranks diverged"
-grads = [torch.zeros_like(local) for _ in range(2)]
-dist.all_gather(grads, local)
+mine = local[0] + local[1]                                     # each already carries loss_scale / accumulation_steps
+grads = [torch.zeros_like(mine) for _ in range(2)]
+dist.all_gather(grads, mine)
 assert not torch.allclose(grads[0], grads[1]), "ranks saw the same data"
-# expected update: AdamW (emulated kernel contract) on the mean of the two local gradients
+# expected update: AdamW (emulated kernel contract) on the mean over ranks of the accumulated gradient
 mean = (grads[0] + grads[1]) / 2
 m, v = torch.zeros_like(mean), torch.zeros_like(mean)
 cpu_emulation.adamw_step(before, mean, m, v, 1, lr=1e-4, grad_norm_sq_t=cpu_emulation.grad_norm_sq(mean),
-                         max_grad_norm=1.0, grad_unscale=1.0 / tr.loss_scale)
+                         max_grad_norm=1.0, grad_unscale=1.0 / tr.loss_scale())
 assert torch.allclose(before, tr.flat_param, rtol=0, atol=2e-7), (before - tr.flat_param).abs().max()
+assert tr.applied_steps() == 1 and tr.skipped_steps() == 0
+# a non-finite gradient: the step is skipped (parameters and moments untouched) and the loss scale halves
+keep, scale0 = tr.flat_param.clone(), tr.loss_scale()
+tr.flat_grad[7] = float("inf"); tr._micro = 2; tr._synced = True
+tr.step()
+assert torch.equal(keep, tr.flat_param) and tr.skipped_steps() == 1 and tr.loss_scale() == scale0 / 2
+# an all-zero gradient (every validity mask empty, train.py:503): skipped too, scale unchanged
+tr._micro = 2; tr._synced = True
+tr.step()
+assert torch.equal(keep, tr.flat_param) and tr.skipped_steps() == 2 and tr.loss_scale() == scale0 / 2
 print("OK", float(loss))
 ''' % (root, root, root)
     ps = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
