@@ -93,14 +93,17 @@ def test_scheduler_matches_oracle_closed_form():
     assert s.timesteps.tolist() == [999, 899, 799, 699, 599, 499, 399, 299, 199, 99]
 
 
-def test_ensemble_normals_bit_exact_vs_oracle():
-    from diffusion_e2e_ft_b200 import ensemble_normals
-    from oracle.pipeline import ensemble_normals as ref
-    g = torch.Generator().manual_seed(1)
-    preds = torch.randn(6, 3, 16, 16, generator=g)
-    got, _ = ensemble_normals(preds)
-    want, idx = ref(preds)
-    assert torch.equal(got, want)
+def test_ensembling_has_no_cpu_fallback():
+    """The ensembling / post-processing ops are device kernels (csrc/postproc.cu; index bit-exactness is checked against
+    the reference-run fixture in tests/test_reference_pins.py on the GPU): a CPU tensor must be refused, not routed
+    through torch arithmetic."""
+    import pytest
+    from diffusion_e2e_ft_b200 import ensemble_depths, ensemble_normals
+    preds = torch.randn(6, 3, 16, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ensemble_normals(preds)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ensemble_depths(preds[:, 0])
 
 
 def test_two_rank_gloo_batch_sharding():
