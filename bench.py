@@ -212,7 +212,7 @@ def cpu_baseline_leg():
 
 
 # --------------------------------------------------------------------------------------------- engine
-def build_engine(device, stream_dtype, module_dtype, workload="marigold", seed=1234):
+def build_engine(device, stream_dtype, module_dtype, workload="marigold", seed=1234, vae_stream_dtype=None):
     import torch
     from diffusion_e2e_ft_b200 import (B200AutoencoderKL, B200UNet2DConditionModel, DDIMScheduler,
                                        DepthNormalEstimationPipeline, MarigoldPipeline)
@@ -226,7 +226,7 @@ def build_engine(device, stream_dtype, module_dtype, workload="marigold", seed=1
                                             joint_attention=True)
         else:
             unet = B200UNet2DConditionModel(stream_dtype=stream_dtype)
-        vae = B200AutoencoderKL(stream_dtype=stream_dtype)
+        vae = B200AutoencoderKL(stream_dtype=vae_stream_dtype or stream_dtype)
     unet.to(module_dtype).eval().requires_grad_(False)
     vae.to(module_dtype).eval().requires_grad_(False)
     if workload == "geowizard":
@@ -379,8 +379,9 @@ def run_engine(args):
     wl = args.workload
     bs = args.batch or {"marigold": 8, "normals": 16, "geowizard": 4}[wl]
     res = args.res
-    sdt = torch.float32 if args.stream == "fp32" else torch.float16
-    pipe = build_engine(dev, sdt, torch.float16, wl)
+    sdt = torch.float16 if args.stream == "fp16" else torch.float32
+    vsdt = torch.float16 if args.stream == "mixed" else None            # mixed: fp32 UNet stream, fp16 VAE stream
+    pipe = build_engine(dev, sdt, torch.float16, wl, vae_stream_dtype=vsdt)
     g = torch.Generator(device="cpu").manual_seed(1000 + rank)
     # the reference API hands the pipeline fp32 images (marigold_pipeline.py:245-247): fp32 pinned host buffers
     host_rgb = (torch.rand(bs, 3, res, res, generator=g) * 2 - 1).pin_memory()
@@ -629,7 +630,8 @@ def main():
                          "configs[3] (bs 4, joint attention); train = configs[2] (bs 2/GPU training step)")
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--res", type=int, default=768)
-    ap.add_argument("--stream", default="fp32", choices=["fp32", "fp16"], help="residual-stream dtype in the engine")
+    ap.add_argument("--stream", default="fp32", choices=["fp32", "mixed", "fp16"],
+                    help="residual-stream dtype in the engine (mixed = fp32 in the UNet, fp16 in the VAE)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[2] training-step leg of the default line")
     ap.add_argument("--no-fast", action="store_true", help="skip the fp16-stream timing of the default line")

@@ -84,7 +84,7 @@ int sm_count() {
 template <int BN, typename OutT, bool SWAP, bool GEGLU = false>
 static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
                       const GemmParams& p, cudaStream_t st) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, SWAP>;
   static bool configured = false;
   auto kern = gemm_conv_kernel<BN, OutT, SWAP, GEGLU>;
   if (!configured) {
@@ -230,7 +230,13 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.act = act; p.alpha = alpha; p.debug = g_debug;
   p.chan_stats = chan_stats; p.rows_per_img = rows_per_img; p.out2 = (__half*)out2_f16;
   p.out_mul = 1;
-  p.vec_ok = 0;
+  // swapped epilogue: 16-byte (fp32) / 8-byte (fp16) accesses over runs of 4 channels
+  {
+    const uintptr_t omask = out_f32 ? 15 : 7;
+    p.vec_ok = swap && N % 4 == 0 && ldo % 4 == 0 && out_batch_stride % 4 == 0 && ((uintptr_t)out & omask) == 0 &&
+               (!residual || (ld_res % 4 == 0 && res_batch_stride % 4 == 0 && ((uintptr_t)residual & omask) == 0)) &&
+               (!out2_f16 || ((uintptr_t)out2_f16 & 7) == 0);
+  }
 
   CUtensorMap ta, tb;
   {
@@ -351,7 +357,8 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   p.act = act; p.alpha = 1.0f; p.debug = g_debug;
   p.chan_stats = out_nchw ? nullptr : chan_stats;
   p.out2 = out_nchw ? nullptr : (__half*)out2_f16;
-  p.vec_ok = (Cout % 8 == 0) && (!residual || ((uintptr_t)residual & 15) == 0);
+  p.vec_ok = swap && (Cout % 4 == 0) && (!residual || ((uintptr_t)residual & 15) == 0) &&
+             (!out2_f16 || ((uintptr_t)out2_f16 & 7) == 0);
 
   CUtensorMap ta, ta2, tb;
   {

@@ -68,14 +68,19 @@ struct GemmParams {
   int debug;                   // perf experiments: 1 = no epilogue stores, 2 = no A loads, 4 = no B loads, 8 = no MMAs, 16 = empty epilogue
 };
 
-template <int BLOCK_N>
+constexpr int kSwapPitch = 36;      // floats per row of the swapped epilogue's transpose tile (16-byte aligned, conflict-free)
+
+template <int BLOCK_N, bool SWAP = false>
 struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kStagingBytes = kEpiWarps * 32 * 33 * 4;   // per-epilogue-warp 32x33 fp32 transpose tile
-  static constexpr int kRowMetaBytes = kEpiWarps * 640;           // per-warp: out offsets, residual offsets, row bias
+  // normal: per-epilogue-warp 32x33 fp32 transpose tile + per-warp row tables (out / residual offsets, row bias)
+  // swapped: pixel-offset tables [2 acc][out|res][BLOCK_N] + flags, then per-warp 32 x kSwapPitch fp32 transpose tiles
+  static constexpr int kSwapTabBytes = 4 * BLOCK_N * 4 + 256;
+  static constexpr int kStagingBytes = SWAP ? kSwapTabBytes + kEpiWarps * 32 * kSwapPitch * 4 : kEpiWarps * 32 * 33 * 4;
+  static constexpr int kRowMetaBytes = SWAP ? 0 : kEpiWarps * 640;
   static constexpr int kEpiBytes = kStagingBytes + kRowMetaBytes;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kBarrierBytes - kEpiBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
@@ -145,7 +150,7 @@ template <int BLOCK_N, typename OutT, bool SWAP, bool GEGLU>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using S = GemmSmem<BLOCK_N>;
+  using S = GemmSmem<BLOCK_N, SWAP>;
   constexpr int kStages = S::kStages;
   // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array itself, so
   // the compiler keeps the shared address space (LDS/STS, no aliasing with global stores)
@@ -342,6 +347,145 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float st1 = 0.f, st2 = 0.f, st_shift = 0.f;     // sums of (v - shift), (v - shift)^2 over this thread's pixels
         int st_cnt = 0;
 
+        if (p.vec_ok) {
+          // ---------------------------------------------------------------- vectorised path (16-byte accesses)
+          // TMEM hands each lane ONE channel of 32 pixels; NHWC wants, per pixel, runs of consecutive channels.  Each
+          // 32x32 chunk goes through a per-warp smem tile (STS.32 by pixel row, LDS.128 back): afterwards lane
+          // (pr = lane / 8, q = lane % 8) owns channels 4q..4q+3 of pixels pr, pr+4, ..., pr+28, so residual loads /
+          // output stores are 16-byte (fp32) or 8-byte (fp16) accesses, four 128-byte pixel rows per warp instruction
+          // — a quarter of the memory instructions of the scalar path.
+          float* stgw = reinterpret_cast<float*>(stage_smem + S::kSwapTabBytes) + ew * (32 * kSwapPitch);
+          const int q = lane & 7, pr = lane >> 3;
+          const int chq = n_blk * kBlockM + quad * 32 + 4 * q;          // first of this lane's four channels
+          const bool cq_ok = chq < p.N;                                 // N % 4 == 0 on this path
+          float add4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (cq_ok) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (bias) add4[k] += bias[chq + k];
+              if (p.rowvec) add4[k] += p.rowvec[(long long)img * p.ld_rowvec + chq + k];
+            }
+          }
+          OutT* __restrict__ out_q = out + (long long)b * p.out_batch_stride + chq;
+          const OutT* __restrict__ res_q = res ? res + (long long)b * p.res_batch_stride + chq : nullptr;
+          __half* __restrict__ out2_q = p.out2 ? p.out2 + (long long)b * p.out_batch_stride + chq : nullptr;
+          using Vec = typename std::conditional<std::is_same<OutT, float>::value, float4, uint2>::type;
+          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+          int scnt = 0;
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + acc * kAccStrideCols + ((uint32_t)(quad * 32) << 16);
+          if (!(p.debug & 16)) {
+#pragma unroll 1
+            for (int c = eg * 32; c < BLOCK_N; c += 64) {
+              uint32_t oo[8];
+              Vec rres[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) oo[i] = cq_ok ? t_out[c + 4 * i + pr] : 0xFFFFFFFFu;
+              if (res_q != nullptr) {                // residual rows first: their latency hides behind the TMEM read
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (oo[i] != 0xFFFFFFFFu) rres[i] = *reinterpret_cast<const Vec*>(res_q + t_res[c + 4 * i + pr]);
+              }
+              uint32_t r[32];
+              tmem_ld_32x32(t_row + c, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) stgw[j * kSwapPitch + lane] = __uint_as_float(r[j]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 t4 = *reinterpret_cast<const float4*>(stgw + (4 * i + pr) * kSwapPitch + 4 * q);
+                float v[4] = {fmaf(t4.x, p.alpha, add4[0]), fmaf(t4.y, p.alpha, add4[1]), fmaf(t4.z, p.alpha, add4[2]),
+                              fmaf(t4.w, p.alpha, add4[3])};
+                float rv4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (res_q != nullptr && oo[i] != 0xFFFFFFFFu) {
+                  if constexpr (std::is_same<OutT, float>::value) {
+                    rv4[0] = rres[i].x; rv4[1] = rres[i].y; rv4[2] = rres[i].z; rv4[3] = rres[i].w;
+                  } else {
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&rres[i].x));
+                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&rres[i].y));
+                    rv4[0] = f0.x; rv4[1] = f0.y; rv4[2] = f1.x; rv4[3] = f1.y;
+                  }
+                }
+                if (res_q != nullptr && !p.res_mul) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) v[k] += rv4[k];
+                }
+                if (p.act == ACT_SILU) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) v[k] = silu_f(v[k]);
+                } else if (p.act == ACT_GELU) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) v[k] = gelu_erf_f(v[k]);
+                }
+                if (res_q != nullptr && p.res_mul) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) v[k] *= rv4[k];
+                }
+                const bool ok = oo[i] != 0xFFFFFFFFu;
+                __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+                uint2 hv;
+                hv.x = *reinterpret_cast<uint32_t*>(&h01);
+                hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                if (ok && !(p.debug & 1)) {
+                  if constexpr (std::is_same<OutT, float>::value) {
+                    *reinterpret_cast<float4*>(out_q + oo[i]) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (out2_q != nullptr) *reinterpret_cast<uint2*>(out2_q + oo[i]) = hv;
+                  } else {
+                    *reinterpret_cast<uint2*>(out_q + oo[i]) = hv;
+                  }
+                }
+                if (p.chan_stats && ok) {
+                  if constexpr (!std::is_same<OutT, float>::value) {      // statistics of the values as stored
+                    const float2 f0 = __half22float2(h01), f1 = __half22float2(h23);
+                    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+                  }
+                  if (scnt == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sh[k] = v[k];
+                  }
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float d = v[k] - sh[k];
+                    s1[k] += d;
+                    s2[k] = fmaf(d, d, s2[k]);
+                  }
+                  ++scnt;
+                }
+              }
+              __syncwarp();                          // the tile is rewritten by the next chunk
+            }
+          }
+          if (p.chan_stats) {
+            // plain sums in fp64 (each lane has its own shift), folded over the four lanes that share a channel quad
+            double d1[4], d2[4];
+            const double n = (double)scnt;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const double shd = (double)sh[k], a = (double)s1[k];
+              d1[k] = a + n * shd;
+              d2[k] = (double)s2[k] + 2.0 * shd * a + n * shd * shd;
+              d1[k] += __shfl_xor_sync(0xffffffffu, d1[k], 8);
+              d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], 8);
+              d1[k] += __shfl_xor_sync(0xffffffffu, d1[k], 16);
+              d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], 16);
+            }
+            if (pr == 0 && cq_ok) {
+              double* dst = p.chan_stats + ((long long)img * p.N + chq) * 2;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                atomicAdd(dst + 2 * k, d1[k]);
+                atomicAdd(dst + 2 * k + 1, d2[k]);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + acc * kAccStrideCols + ((uint32_t)(quad * 32) << 16);

@@ -1,5 +1,7 @@
 // HBM-bound normalisation kernels: GroupNorm (two-pass, NHWC, fused concat + SiLU), LayerNorm,
 // row softmax.  16-byte vectorised coalesced loads, warp-shuffle reductions, fp32 statistics.
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/b200_e2eft.h"
 
@@ -166,22 +168,46 @@ __global__ void gn_apply_kernel(const T* __restrict__ x1, int C1, const T* __res
   const int p1 = min(HW, p0 + pix_per_cta);
   __half* yb = y + (long long)n * HW * C + c0;
   __half* rb = raw ? raw + (long long)n * HW * C + c0 : nullptr;
-  // 8 pixels per iteration: eight independent 16/32-byte loads in flight per thread (latency-bound otherwise)
+  // 8 pixels per iteration: eight independent 16/32-byte loads in flight per thread (latency-bound otherwise).  The
+  // loaded vectors stay in their storage type until use (fp16 input: 4 registers per pixel instead of 8), which keeps
+  // the fp16 instantiation under 85 registers = three 256-thread CTAs per SM (ncu r2: 119 registers / 2 CTAs, 81 % of
+  // the HBM roofline).
+  using Raw = typename std::conditional<sizeof(T) == 2, uint4, float4>::type;
+  constexpr int kRawPerPix = sizeof(T) == 2 ? 1 : 2;
+  auto unpack = [](const Raw* rv, float* f) {
+    if constexpr (sizeof(T) == 2) {
+      const __half2* h = reinterpret_cast<const __half2*>(rv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+      }
+    } else {
+      f[0] = rv[0].x; f[1] = rv[0].y; f[2] = rv[0].z; f[3] = rv[0].w;
+      f[4] = rv[1].x; f[5] = rv[1].y; f[6] = rv[1].z; f[7] = rv[1].w;
+    }
+  };
   int p = p0 + r;
   for (; p + 7 * rpb < p1; p += 8 * rpb) {
-    float f[8][8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) load8(base + (long long)(p + u * rpb) * ld, f[u]);
+    Raw raw[8][kRawPerPix];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      float o[8];
+      const Raw* src = reinterpret_cast<const Raw*>(base + (long long)(p + u * rpb) * ld);
+#pragma unroll
+      for (int k = 0; k < kRawPerPix; ++k) raw[u][k] = src[k];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float f[8], o[8];
+      unpack(raw[u], f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float t = f[u][e] * a[e] + b[e];
+        float t = f[e] * a[e] + b[e];
         o[e] = silu ? __fdividef(t, 1.0f + __expf(-t)) : t;
       }
       store8h(yb + (long long)(p + u * rpb) * C, o);
-      if (rb) store8h(rb + (long long)(p + u * rpb) * C, f[u]);
+      if (rb) store8h(rb + (long long)(p + u * rpb) * C, f);
     }
   }
   for (; p < p1; p += rpb) {

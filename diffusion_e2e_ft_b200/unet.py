@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import ops
 from .modules import (ConfigDict, ConvInSmall, ConvOutSmall, Downsample2D, Packed, ResnetBlock2D,
                       Transformer2DModel, Upsample2D, _f16, _f32)
+from .checkpoint import PretrainedMixin
 from .ops import F16, F32
 
 
@@ -81,8 +82,10 @@ _DEFAULTS = dict(
     flip_sin_to_cos=True, freq_shift=0, sample_size=96, act_fn="silu", use_linear_projection=True)
 
 
-class B200UNet2DConditionModel(nn.Module):
+class B200UNet2DConditionModel(PretrainedMixin, nn.Module):
     """`stream_dtype`: dtype of the residual stream inside the engine (fp32 = parity mode, fp16 = fast)."""
+    _diffusers_class_name = "UNet2DConditionModel"
+    _config_defaults = _DEFAULTS
 
     def __init__(self, stream_dtype=torch.float32, **config):
         super().__init__()
@@ -91,6 +94,9 @@ class B200UNet2DConditionModel(nn.Module):
         if unknown:
             raise TypeError(f"unknown UNet config keys: {sorted(unknown)}")
         cfg.update(config)
+        for k in ("block_out_channels", "down_block_types", "up_block_types", "attention_head_dim"):
+            if isinstance(cfg[k], list):
+                cfg[k] = tuple(cfg[k])
         if not cfg["flip_sin_to_cos"] or cfg["freq_shift"] != 0 or not cfg["use_linear_projection"]:
             raise NotImplementedError("engine supports the SD-2 embedding / linear-projection config only")
         self.config = cfg
@@ -140,7 +146,11 @@ class B200UNet2DConditionModel(nn.Module):
         self._gradient_checkpointing = True
 
     def register_to_config(self, **kw):
-        self.config.update(kw)
+        """diffusers API used by the load hook (training/train.py:335): unknown keys are kept, not rejected."""
+        self.config.update({k: v for k, v in kw.items() if k in _DEFAULTS})
+        extra = {k: v for k, v in kw.items() if k not in _DEFAULTS and k != "_extra"}
+        if extra:
+            self.config.setdefault("_extra", {}).update(extra)
 
     def _resnets(self):
         for blk in self.down_blocks:

@@ -12,6 +12,7 @@ import torch.nn as nn
 from . import ops
 from .modules import (ConfigDict, ConvInSmall, ConvOutSmall, Downsample2D, Packed, ResnetBlock2D,
                       Upsample2D, _f16, _f32, _view_cs)
+from .checkpoint import PretrainedMixin
 from .ops import F16, F32
 
 _DEFAULTS = dict(in_channels=3, out_channels=3, latent_channels=4,
@@ -203,7 +204,10 @@ class Conv1x1Small(nn.Conv2d):
         return out if out.dtype == x.dtype else out.to(x.dtype)
 
 
-class B200AutoencoderKL(nn.Module):
+class B200AutoencoderKL(PretrainedMixin, nn.Module):
+    _diffusers_class_name = "AutoencoderKL"
+    _config_defaults = _DEFAULTS
+
     def __init__(self, stream_dtype=torch.float32, **config):
         super().__init__()
         cfg = ConfigDict(_DEFAULTS)
@@ -227,7 +231,7 @@ class B200AutoencoderKL(nn.Module):
         return next(self.parameters()).device
 
     def register_to_config(self, **kw):
-        self.config.update(kw)
+        self.config.update({k: v for k, v in kw.items() if k in _DEFAULTS})
 
     # ---- fused conveniences used by the engine's own pipelines (same math as the call sites above)
     def encode_scaled_mean(self, rgb):

@@ -45,7 +45,7 @@ def absrel_protocol(pred_engine, pred_oracle, noise=0.05, seed=0):
     return dict(absrel_engine=ar_e, absrel_oracle=ar_o, absrel_delta=abs(ar_e - ar_o))
 
 
-def engine_from_oracle(unet_ref, vae_ref, device, stream_dtype=torch.float32, dtype=torch.float32):
+def engine_from_oracle(unet_ref, vae_ref, device, stream_dtype=torch.float32, dtype=torch.float32, vae_stream_dtype=None):
     cfg = unet_ref.config
     unet = B200UNet2DConditionModel(
         stream_dtype=stream_dtype, in_channels=cfg.in_channels, block_out_channels=cfg.block_out_channels,
@@ -56,7 +56,8 @@ def engine_from_oracle(unet_ref, vae_ref, device, stream_dtype=torch.float32, dt
     unet.load_state_dict(unet_ref.state_dict(), strict=True)
     vae = None
     if vae_ref is not None:
-        vae = B200AutoencoderKL(stream_dtype=stream_dtype, block_out_channels=vae_ref.config.block_out_channels)
+        vae = B200AutoencoderKL(stream_dtype=vae_stream_dtype or stream_dtype,
+                                block_out_channels=vae_ref.config.block_out_channels)
         vae.load_state_dict(vae_ref.state_dict(), strict=True)
         vae = vae.to(device=device, dtype=dtype).eval().requires_grad_(False)
     return unet.to(device=device, dtype=dtype).eval().requires_grad_(False), vae
@@ -151,7 +152,7 @@ def run_unet_fullwidth(device="cuda:0", latent=24, batch=1, stream_dtype=torch.f
 
 
 @torch.no_grad()
-def run_full_size(device="cuda:0", res=768, batch=1, stream_dtype=torch.float32):
+def run_full_size(device="cuda:0", res=768, batch=1, stream_dtype=torch.float32, vae_stream_dtype=None):
     """BASELINE.json full size: 768x768, SD-2 widths.  The oracle itself is run in fp32 on the GPU with plain
     torch ops (test infrastructure) so the comparison finishes in seconds; also checks size-independent
     properties (range of depth, unit normals, batch consistency)."""
@@ -161,7 +162,7 @@ def run_full_size(device="cuda:0", res=768, batch=1, stream_dtype=torch.float32)
     torch.backends.cudnn.allow_tf32 = False
     uref = seeded_init(UNet2DConditionRef(UNetConfig()), seed=4321).eval()
     vref = seeded_init(AutoencoderKLRef(VAEConfig()), seed=99).eval()
-    unet, vae = engine_from_oracle(uref, vref, device, stream_dtype)
+    unet, vae = engine_from_oracle(uref, vref, device, stream_dtype, vae_stream_dtype=vae_stream_dtype)
     uref, vref = uref.to(device), vref.to(device)
     g = torch.Generator().manual_seed(7)
     rgb = (torch.rand(batch, 3, res, res, generator=g) * 2 - 1).to(device)

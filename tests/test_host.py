@@ -145,3 +145,33 @@ print("OK")
           for r in range(2)]
     outs = [p.communicate(timeout=180) for p in ps]
     assert all(p.returncode == 0 for p in ps), outs
+
+
+def test_save_pretrained_from_pretrained_round_trip(tmp_path):
+    """training/train.py:322-339,610-630: the accelerate save / load hooks call `save_pretrained` / `from_pretrained`
+    / `register_to_config(**config)` / `load_state_dict` on the UNet — diffusers directory layout (config.json +
+    diffusion_pytorch_model.safetensors), diffusers parameter names, unknown config keys preserved."""
+    import json
+    from diffusion_e2e_ft_b200 import B200AutoencoderKL, B200UNet2DConditionModel
+    unet = B200UNet2DConditionModel(block_out_channels=(64, 128, 256, 256), attention_head_dim=(1, 2, 4, 4),
+                                    cross_attention_dim=128)
+    d = tmp_path / "ckpt"
+    unet.save_pretrained(str(d / "unet"))                                      # the save hook's call
+    cfg = json.load(open(d / "unet" / "config.json"))
+    assert cfg["_class_name"] == "UNet2DConditionModel" and cfg["block_out_channels"] == [64, 128, 256, 256]
+    assert (d / "unet" / "diffusion_pytorch_model.safetensors").exists()
+    cfg["dropout"] = 0.0                                                       # a diffusers key the engine does not model
+    json.dump(cfg, open(d / "unet" / "config.json", "w"))
+    load_model = B200UNet2DConditionModel.from_pretrained(str(d), subfolder="unet")    # the load hook's calls
+    fresh = B200UNet2DConditionModel(block_out_channels=(64, 128, 256, 256), attention_head_dim=(1, 2, 4, 4),
+                                     cross_attention_dim=128)
+    fresh.register_to_config(**load_model.config)
+    fresh.load_state_dict(load_model.state_dict())
+    for (k, a), (_, b) in zip(unet.state_dict().items(), fresh.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert load_model.config["_extra"]["dropout"] == 0.0 and load_model.config["cross_attention_dim"] == 128
+    vae = B200AutoencoderKL(block_out_channels=(64, 64, 128, 128))
+    vae.save_pretrained(str(d / "vae"), safe_serialization=False)
+    v2 = B200AutoencoderKL.from_pretrained(str(d / "vae"), torch_dtype=torch.float16)
+    assert v2.dtype == torch.float16 and v2.config["block_out_channels"] == (64, 64, 128, 128)
+    assert torch.equal(v2.state_dict()["decoder.conv_in.weight"], vae.state_dict()["decoder.conv_in.weight"].half())
