@@ -120,6 +120,45 @@ def check_conv(NB=2, H=24, W=24, Cin=128, Cout=192, stride=1, pad_mode="same", s
     return err, tol or (3e-5 if out_f32 else 1e-3)
 
 
+def check_swap_epilogue_twins(seed=51):
+    """Vectorised swapped epilogue: fp32 output + fp16 twin + fused per-channel statistics + SiLU + fp32 residual on a
+    ragged conv (odd pixel count, Cout = 320 = 2.5 channel tiles), and a fp16-output linear with a multiplicative
+    fp16 residual operand and N = 960.  Output, twin and statistics against torch."""
+    NB, H, W, Cin, Cout = 2, 15, 21, 64, 320
+    x = _rand(NB, H, W, Cin, seed=seed)
+    w = _rand(Cout, Cin, 3, 3, seed=seed + 1, scale=1.0 / math.sqrt(9 * Cin))
+    b = _rand(Cout, seed=seed + 2, dtype=torch.float32)
+    res = _rand(NB, H, W, Cout, seed=seed + 3, dtype=torch.float32)
+    L = ops._lib.load()
+    L.b200_debug_force_block_n(256)          # 256-wide candidates only: the cost model then takes the swapped orientation
+    try:
+        out = ops.conv2d(x, ops.pack_conv(w), Cout, bias=b, residual=res, out_dtype=torch.float32, act=ops.ACT_SILU,
+                         stats=True, f16_copy=True)
+        torch.cuda.synchronize()
+    finally:
+        L.b200_debug_force_block_n(0)
+    ref = F.silu(_conv_ref(x, w, b, 1, "same").permute(0, 2, 3, 1) + res)
+    e1 = rel_l2(out, ref)
+    e2 = rel_l2(out._h16, out.half())
+    cs = out._cs.float()                                                   # [NB, Cout, 2] (sum, sum of squares)
+    want = torch.stack([out.double().sum((1, 2)), (out.double() ** 2).sum((1, 2))], -1).float()
+    e3 = rel_l2(cs, want)
+    M, N, K = 1000, 960, 320
+    a = _rand(M, K, seed=seed + 4)
+    w2 = _rand(N, K, seed=seed + 5, scale=1.0 / math.sqrt(K))
+    b2 = _rand(N, seed=seed + 6, dtype=torch.float32)
+    gate = _rand(M, N, seed=seed + 7)
+    L.b200_debug_force_block_n(128)
+    try:
+        o2 = ops.linear(a, w2, b2, residual=gate, res_mul=True)
+        torch.cuda.synchronize()
+    finally:
+        L.b200_debug_force_block_n(0)
+    ref2 = (a.float() @ w2.float().t() + b2) * gate.float()
+    e4 = rel_l2(o2, ref2)
+    return max(e1 / 3e-5, e2 / 1e-7 if e2 > 0 else 0.0, e3 / 1e-5, e4 / 1e-3) * 1e-3, 1e-3
+
+
 def check_upsample_conv_phases(NB=2, H=12, W=10, C=128, seed=21):
     """Upsample2D: nearest x2 + conv3x3 computed as four 2x2 convs on the low-res input."""
     from diffusion_e2e_ft_b200.modules import Upsample2D
@@ -529,6 +568,7 @@ CHECKS = {
     "conv_swap_odd": lambda: check_conv(NB=1, H=15, W=20, Cin=64, Cout=128, residual=True),
     "conv_swap_768": lambda: check_conv(NB=1, H=96, W=768, Cin=128, Cout=128, seed=9),
     "conv_swap_1280_12": lambda: check_conv(NB=2, H=12, W=12, Cin=256, Cout=1280),
+    "swap_epilogue_twins_stats": check_swap_epilogue_twins,
     "conv_noswap_256": _noswap(lambda: check_conv(H=24, W=24, Cin=128, Cout=256, residual=True, out_f32=True)),
     "linear_noswap_1280": _noswap(lambda: check_linear(M=2000, N=1280, K=1280, residual=True, seed=2)),
     "linear_swap_small_m": lambda: check_linear(M=8, N=1280, K=1280, act=ops.ACT_SILU),
