@@ -147,21 +147,28 @@ def test_cuda_ensemble_depths_matches_reference(pins):
 
 @pytest.mark.gpu
 def test_cuda_replace_unet_conv_in_on_engine_unet(pins):
-    """training/util/unet_prep.py:6-21 applied by the reference's own rule to the ENGINE module: duplicated input halves
-    reproduce the 4-channel output (the identity the reference relies on)."""
+    """training/util/unet_prep.py:6-21 (weights duplicated, weights AND bias divided by `repeat`) applied by the same
+    rule to the ENGINE module and to the oracle: the widened engine UNet must match the widened oracle UNet, and —
+    because the bias is halved too (a reference quirk) — it must NOT reproduce the 4-channel output."""
     import make_golden as MG
     import engine_checks as EC
     from oracle.unet import UNet2DConditionRef, tiny_config, seeded_init
     ref4 = seeded_init(UNet2DConditionRef(tiny_config(in_channels=4)), seed=1234).eval()
     unet, _ = EC.engine_from_oracle(ref4, None, "cuda:0")
     x4 = MG.inputs(31, 2, 4, 16, 16)
+    x8 = torch.cat([x4, x4], 1)
     ctx = MG.inputs(32, 2, 2, 128, scale=0.5)
     with torch.no_grad():
         y4 = unet(x4.cuda(), 999, ctx.cuda()).sample
+        assert EC.rel_l2(y4, ref4(x4, 999, ctx).sample) <= 3e-3
         replace_unet_conv_in(unet, repeat=2)
+        replace_unet_conv_in(ref4, repeat=2)
         assert unet.config["in_channels"] == 8 and unet.conv_in.weight.shape[1] == 8
-        y8 = unet(torch.cat([x4, x4], 1).cuda(), 999, ctx.cuda()).sample
-    assert EC.rel_l2(y8, y4) <= 2e-3
+        assert torch.equal(unet.conv_in.weight.detach().cpu(), ref4.conv_in.weight.detach())
+        y8 = unet(x8.cuda(), 999, ctx.cuda()).sample
+        want8 = ref4(x8, 999, ctx).sample
+    assert EC.rel_l2(y8, want8) <= 3e-3
+    assert EC.rel_l2(y8, y4) > 1e-2                      # halved bias: the widened model is a different function
 
 
 @pytest.mark.gpu
@@ -175,7 +182,7 @@ def test_cuda_preprocessing_matches_torchvision_semantics():
     for size in ((360, 480), (576, 768), (97, 131), (480, 640)):
         want = F.interpolate(img[None].float(), size=size, mode="bilinear", antialias=True, align_corners=False)[0]
         got = resize_bilinear_aa(img.cuda().float(), size)
-        assert (got.cpu() - want).abs().max().item() <= 2e-3, size                  # values in [0, 255]
+        assert (got.cpu() - want).abs().max().item() <= 1e-2, size                  # values in [0, 255]: 4e-5 relative
         want_n = torch.round(want).clamp(0, 255) / 255.0 * 2.0 - 1.0
         got_n = normalise_rgb(got, round_u8=True).cpu()
         assert ((got_n - want_n).abs() > 1e-6).float().mean().item() <= 1e-4, size  # a rounding tie may flip one level
