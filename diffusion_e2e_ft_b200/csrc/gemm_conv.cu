@@ -81,12 +81,12 @@ int sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------
-template <int BN, typename OutT, bool SWAP, bool GEGLU = false>
+template <int BN, typename OutT, bool SWAP, bool GEGLU = false, bool HALO = false>
 static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
                       const GemmParams& p, cudaStream_t st) {
-  using S = GemmSmem<BN, SWAP>;
+  using S = GemmSmem<BN, SWAP, HALO>;
   static bool configured = false;
-  auto kern = gemm_conv_kernel<BN, OutT, SWAP, GEGLU>;
+  auto kern = gemm_conv_kernel<BN, OutT, SWAP, GEGLU, HALO>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes);
     if (e != cudaSuccess) {
@@ -146,6 +146,31 @@ static double tiles_cost(long long tiles, int n) {
 static int g_force_bn = 0;
 static int g_debug = 0;
 static int g_swap_mode = 1;   // 1 = automatic (swap operands when Cout % 128 == 0), 0 = never
+static int g_halo_mode = 1;   // 1 = automatic (halo-resident patch for stride-1 3x3 convs), 0 = never
+static int g_last_path = 0;   // 0 = per-tap boxes / GEMM, 1 = halo-resident conv (tests assert the path they mean to cover)
+
+// Tile geometry of the halo-resident conv: bh rows x bw columns of output pixels, one MMA (N = bw) per row and k-step.
+// bw % 16 == 0 (UMMA N granularity at M = 128), bw * bh <= 256 accumulator columns, (bw+2)(bh+2) <= kHaloMaxPatchPix.
+static bool pick_halo_tile(int Ho, int Wo, int* bw_out, int* bh_out) {
+  double best = 0.0;
+  int bbw = 0, bbh = 0;
+  const int cands[7] = {128, 112, 96, 80, 64, 48, 32};
+  for (int ci = 0; ci < 7; ++ci) {
+    const int bw = cands[ci];
+    if (bw > ((Wo + 15) / 16) * 16) continue;
+    for (int bh = 1; bh <= 8; ++bh) {
+      if (bw * bh > 256 || (bw + 2) * (bh + 2) > kHaloMaxPatchPix || bh > Ho) continue;
+      const double ew = (double)Wo / ((double)((Wo + bw - 1) / bw) * bw);
+      const double eh = (double)Ho / ((double)((Ho + bh - 1) / bh) * bh);
+      double score = ew * eh * (0.75 + 0.25 * (bw * bh) / 256.0);       // mild preference for full tiles
+      if (bw < 64) score *= (bw == 48 ? 0.93 : 0.85);                   // short MMAs (N < 64) are issue-bound
+      score *= 1.0 - 0.02 * ((double)(bw + 2) * (bh + 2) / (bw * bh) - 1.0);   // halo traffic
+      if (score > best + 1e-9) { best = score; bbw = bw; bbh = bh; }
+    }
+  }
+  *bw_out = bbw; *bh_out = bbh;
+  return bbw != 0 && best >= 0.80;
+}
 
 }  // namespace b200
 
@@ -155,6 +180,8 @@ extern "C" const char* b200_last_error_string(void) { return b200::last_error();
 extern "C" void b200_debug_force_block_n(int bn) { b200::g_force_bn = bn; }
 extern "C" void b200_debug_set_flags(int f) { b200::g_debug = f; }
 extern "C" void b200_debug_set_swap(int m) { b200::g_swap_mode = m; }
+extern "C" void b200_debug_set_halo(int m) { b200::g_halo_mode = m; }
+extern "C" int b200_debug_last_path(void) { return b200::g_last_path; }
 extern "C" int b200_abi_version(void) { return 2; }
 // Tile width used by the GEGLU epilogue for a packed width N (= 2 x output width); weights must be
 // packed per tile as [value half | gate half] with this width.
@@ -304,6 +331,62 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   p.batch = 1;
   p.Ho = Ho; p.Wo = Wo;
   const bool can_swap = g_swap_mode && Cout >= 128 && !out_nchw;
+  // ---- halo-resident path: stride-1 "same" 3x3 convs in the swapped orientation
+  {
+    bool taps_ok = num_taps == 9 && stride == 1 && out_mul == 1 && Ho == H && Wo == W;
+    for (int i = 0; i < 9 && taps_ok; ++i) taps_ok = tap_dy[i] == i / 3 - 1 && tap_dx[i] == i % 3 - 1;
+    int hbw = 0, hbh = 0;
+    if (can_swap && g_halo_mode && taps_ok && !g_force_bn && Wo >= 32 && pick_halo_tile(Ho, Wo, &hbw, &hbh)) {
+      p.bw = hbw; p.bh = hbh;
+      p.tiles_w = (Wo + hbw - 1) / hbw;
+      p.tiles_h = (Ho + hbh - 1) / hbh;
+      p.m_tiles = NB * p.tiles_w * p.tiles_h;
+      p.n_tiles = (Cout + 127) / 128;
+      p.M = NB * Ho * Wo;
+      p.cin_blocks = Cin / 64;
+      p.num_taps = 9;
+      p.in_stride = 1;
+      p.k2_blocks = X2 ? C2 / 64 : 0;
+      p.num_k_blocks = 9 * p.cin_blocks + p.k2_blocks;
+      p.out_mul = 1; p.out_oy = 0; p.out_ox = 0; p.OH = Ho; p.OW = Wo;
+      p.out = out; p.ldo = Cout; p.out_f32 = out_f32; p.out_nchw = 0;
+      p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec;
+      p.residual = residual; p.ld_res = Cout;
+      p.act = act; p.alpha = 1.0f; p.debug = g_debug;
+      p.chan_stats = chan_stats; p.out2 = (__half*)out2_f16;
+      p.vec_ok = (Cout % 4 == 0) && (!residual || ((uintptr_t)residual & 15) == 0) &&
+                 (!out2_f16 || ((uintptr_t)out2_f16 & 7) == 0);
+      CUtensorMap ta, ta2, tb;
+      {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+        uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        uint32_t box[4] = {kBlockK, (uint32_t)(hbw + 2), (uint32_t)(hbh + 2), 1};
+        int r = encode_tmap(&ta, X, 4, dims, str, box, nullptr);
+        if (r) return r;
+      }
+      ta2 = ta;
+      if (X2) {
+        uint64_t dims[4] = {(uint64_t)C2, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NB};
+        uint64_t str[3] = {(uint64_t)C2 * 2, (uint64_t)Wo * C2 * 2, (uint64_t)Ho * Wo * C2 * 2};
+        uint32_t box[4] = {kBlockK, (uint32_t)(hbw + 2), (uint32_t)(hbh + 2), 1};
+        int r = encode_tmap(&ta2, X2, 4, dims, str, box, nullptr);
+        if (r) return r;
+      }
+      {
+        const long long Kt = 9LL * Cin + (X2 ? C2 : 0);
+        uint64_t dims[3] = {(uint64_t)Kt, (uint64_t)Cout, 1};
+        uint64_t str[2] = {(uint64_t)Kt * 2, (uint64_t)Kt * Cout * 2};
+        uint32_t box[3] = {kBlockK, (uint32_t)kBlockM, 1};
+        int r = encode_tmap(&tb, Wp, 3, dims, str, box, nullptr);
+        if (r) return r;
+      }
+      cudaStream_t st = (cudaStream_t)stream;
+      g_last_path = 1;
+      return out_f32 ? launch_one<256, float, true, false, true>(ta, ta2, tb, p, st)
+                     : launch_one<256, __half, true, false, true>(ta, ta2, tb, p, st);
+    }
+  }
+  g_last_path = 0;
   bool swap = false;
   int pix = 128, bn_norm = 0;
   {

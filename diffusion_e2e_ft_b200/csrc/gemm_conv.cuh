@@ -70,7 +70,16 @@ struct GemmParams {
 
 constexpr int kSwapPitch = 36;      // floats per row of the swapped epilogue's transpose tile (16-byte aligned, conflict-free)
 
-template <int BLOCK_N, bool SWAP = false>
+// HALO (conv3x3, stride 1, swapped orientation): the activation patch of a tile — (bh+2) x (bw+2) pixels x 64 channels —
+// is loaded ONCE per 64-channel block and all nine taps are issued as row-shifted views of it (UMMA descriptors with a
+// 128-byte-granular start address), instead of nine separate bw x bh boxes: 9x -> (bh+2)(bw+2)/(bh*bw) ~ 1.5x of
+// L2 -> smem activation traffic.  Measured motivation (profiles/conv_isolation_r02.txt): with the operand loads
+// removed the same MMA / epilogue schedule runs 1.5x faster (1047 -> 1567 TFLOP/s on the 128-ch 768^2 conv).
+constexpr int kHaloMaxPatchPix = 400;                       // (bw+2)*(bh+2) <= 400: 64x4, 96x2, 48x5, 32x8 tiles
+constexpr int kHaloPatchBytes = kHaloMaxPatchPix * 128;     // one 64-channel slab of the patch (50 KB, 1024-aligned)
+constexpr int kHaloWStages = 5;                             // 128 x 64 weight tiles in flight (16 KB each)
+
+template <int BLOCK_N, bool SWAP = false, bool HALO = false>
 struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -83,8 +92,10 @@ struct GemmSmem {
   static constexpr int kRowMetaBytes = SWAP ? 0 : kEpiWarps * 640;
   static constexpr int kEpiBytes = kStagingBytes + kRowMetaBytes;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kBarrierBytes - kEpiBytes;
-  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
-  static constexpr int kTotalBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;
+  static constexpr int kStages = HALO ? kHaloWStages : ((kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes));
+  static constexpr int kOperandBytes = HALO ? kHaloWStages * kABytes + 2 * kHaloPatchBytes : kStages * kStageBytes;
+  static constexpr int kTotalBytes = kOperandBytes + kEpiBytes + kBarrierBytes + 1024;
+  static_assert(kTotalBytes <= 227 * 1024, "shared memory budget");
 };
 
 template <typename OutT>
@@ -146,26 +157,29 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 //               layer then issues 128x256 MMAs (half the operand smem traffic and half the per-k-block
 //               barrier round trips of 128x128), and since lanes = channels the NHWC stores of one
 //               accumulator column are contiguous — no smem transpose in the epilogue.
-template <int BLOCK_N, typename OutT, bool SWAP, bool GEGLU>
+template <int BLOCK_N, typename OutT, bool SWAP, bool GEGLU, bool HALO = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using S = GemmSmem<BLOCK_N, SWAP>;
+  static_assert(!HALO || (SWAP && !GEGLU && BLOCK_N == 256), "halo mode: swapped orientation, 256 accumulator columns");
+  using S = GemmSmem<BLOCK_N, SWAP, HALO>;
   constexpr int kStages = S::kStages;
   // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array itself, so
   // the compiler keeps the shared address space (LDS/STS, no aliasing with global stores)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * S::kABytes;
-  uint8_t* stage_smem = smem + kStages * S::kStageBytes;
+  uint8_t* smem_a = smem;                                // HALO: the weight-tile ring
+  uint8_t* smem_b = smem + kStages * S::kABytes;         // HALO: the two patch buffers
+  uint8_t* stage_smem = smem + S::kOperandBytes;
   uint8_t* rowmeta_smem = stage_smem + S::kStagingBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kEpiBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOperandBytes + S::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + kAccStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
+  uint64_t* patch_full = bars + 2 * kStages + 2 * kAccStages + 1;      // HALO only
+  uint64_t* patch_empty = patch_full + 2;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,6 +203,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kEpiWarps);
     }
+    if constexpr (HALO) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&patch_full[i], 1);
+        mbar_init(&patch_empty[i], 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
@@ -199,6 +219,44 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ======================================================================= TMA producer
+    if constexpr (HALO) {
+      if (lane == 0) {
+        int ws = 0, pb = 0;
+        uint32_t wphase = 0, pphase = 0;
+        const uint32_t patch_bytes = (uint32_t)((p.bw + 2) * (p.bh + 2) * kBlockK * 2);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int n_blk = tile % p.n_tiles;                       // channel tile (fastest: neighbours share the patch in L2)
+          const int m_blk = tile / p.n_tiles;
+          const int tw = m_blk % p.tiles_w;
+          const int r2 = m_blk / p.tiles_w;
+          const int th = r2 % p.tiles_h;
+          const int img = r2 / p.tiles_h;
+          const int h0 = th * p.bh, w0 = tw * p.bw;
+          for (int blk = 0; blk < p.cin_blocks + p.k2_blocks; ++blk) {
+            const bool main = blk < p.cin_blocks;
+            mbar_wait(&patch_empty[pb], pphase ^ 1);
+            mbar_arrive_expect_tx(&patch_full[pb], patch_bytes);
+            // one box = the whole (bh+2) x (bw+2) halo patch of this 64-channel block; image borders = OOB zero fill
+            if (main)
+              tma_load_4d(&tmA, &patch_full[pb], smem_b + pb * kHaloPatchBytes, blk * kBlockK, w0 - 1, h0 - 1, img,
+                          kEvictNormal);
+            else
+              tma_load_4d(&tmA2, &patch_full[pb], smem_b + pb * kHaloPatchBytes, (blk - p.cin_blocks) * kBlockK, w0 - 1,
+                          h0 - 1, img, kEvictNormal);
+            const int ntaps = main ? 9 : 1;                         // the 1x1 shortcut operand only feeds the centre tap
+            for (int t = 0; t < ntaps; ++t) {
+              const int kcol = main ? (t * p.cin_blocks + blk) : (9 * p.cin_blocks + (blk - p.cin_blocks));
+              mbar_wait(&empty_bar[ws], wphase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[ws], (uint32_t)S::kABytes);
+              tma_load_3d(&tmB, &full_bar[ws], smem_a + ws * S::kABytes, kcol * kBlockK, n_blk * kBlockM, 0, kEvictLast);
+              if (++ws == kStages) { ws = 0; wphase ^= 1; }
+            }
+            pb ^= 1;
+            if (pb == 0) pphase ^= 1;
+          }
+        }
+      }
+    } else
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -252,6 +310,53 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
     constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, 0, 0);
+    if constexpr (HALO) {
+      if (lane == 0) {
+        int ws = 0, pb = 0, acc = 0;
+        uint32_t wphase = 0, pphase = 0, acc_phase = 0;
+        const uint32_t a_base = smem_u32(smem_a), patch_base = smem_u32(smem_b);
+        const uint32_t idesc_row = make_idesc_f16(kBlockM, (uint32_t)p.bw, 0, 0);      // one MMA = one output row of bw pixels
+        const int pitch = p.bw + 2;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kAccStrideCols;
+          for (int blk = 0; blk < p.cin_blocks + p.k2_blocks; ++blk) {
+            const bool main = blk < p.cin_blocks;
+            mbar_wait(&patch_full[pb], pphase);
+            tc_fence_after();
+            const uint32_t pbase = patch_base + pb * kHaloPatchBytes;
+            const int ntaps = main ? 9 : 1;
+            for (int t = 0; t < ntaps; ++t) {
+              const int tap = main ? t : 4;
+              const int dy = tap / 3, dx = tap - 3 * dy;              // patch offsets (0..2): tap (dy-1, dx-1)
+              mbar_wait(&full_bar[ws], wphase);
+              tc_fence_after();
+              const uint64_t adesc = make_desc_sw128(a_base + ws * S::kABytes, 16, 1024);
+              for (int r = 0; r < p.bh; ++r) {
+                // B operand rows = patch pixels ((r+dy)*pitch + dx) ... + bw: a 128-byte-granular start inside the
+                // SWIZZLE_128B tile; the descriptor's base-offset field carries (start >> 7) & 7 (tools/micro/
+                // umma_rowoffset_test.cu)
+                const uint32_t baddr = pbase + (uint32_t)(((r + dy) * pitch + dx) * 128);
+                uint64_t bdesc = make_desc_sw128(baddr, 16, 1024);
+                if (!(p.debug & 32)) bdesc |= (uint64_t)((baddr >> 7) & 7) << 49;
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  if (!(p.debug & 8))
+                    umma_f16(d_tmem + r * p.bw, adesc + 2 * k, bdesc + 2 * k, idesc_row, (blk | t | k) != 0);
+              }
+              umma_commit(&empty_bar[ws]);
+              if (++ws == kStages) { ws = 0; wphase ^= 1; }
+            }
+            umma_commit(&patch_empty[pb]);
+            pb ^= 1;
+            if (pb == 0) pphase ^= 1;
+          }
+          umma_commit(&tmem_full[acc]);
+          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else
     if (lane == 0) {            // a single thread runs the whole issue loop (no warp-wide polling / syncs)
       int stage = 0;
       uint32_t phase = 0;
@@ -375,9 +480,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&tmem_full[acc], acc_phase);
           tc_fence_after();
           const uint32_t t_row = tmem_base + acc * kAccStrideCols + ((uint32_t)(quad * 32) << 16);
+          // conv tiles may use fewer than BLOCK_N accumulator columns (bw * bh pixels)
+          const int ncols = p.conv ? min(BLOCK_N, (p.bw * p.bh + 31) & ~31) : BLOCK_N;
           if (!(p.debug & 16)) {
 #pragma unroll 1
-            for (int c = eg * 32; c < BLOCK_N; c += 64) {
+            for (int c = eg * 32; c < ncols; c += 64) {
               uint32_t oo[8];
               Vec rres[8];
 #pragma unroll

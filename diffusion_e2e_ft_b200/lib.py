@@ -21,6 +21,8 @@ _SIGS = {
     "b200_debug_force_block_n": (None, [c_int]),
     "b200_debug_set_flags": (None, [c_int]),
     "b200_debug_set_swap": (None, [c_int]),
+    "b200_debug_set_halo": (None, [c_int]),
+    "b200_debug_last_path": (c_int, []),
     "b200_geglu_block_n": (c_int, [c_int]),
     "b200_linear": (c_int, [_P, _LL, _LL, _P, _LL, _LL, c_int, c_int, c_int, c_int, _P, c_int, _P, _LL, _LL,
                             _P, _LL, _LL, c_int, c_int, c_float, _P, c_int, _P, c_int, _P]),

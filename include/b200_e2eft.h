@@ -258,6 +258,8 @@ void b200_debug_force_block_n(int bn);
 void b200_debug_set_flags(int flags);
 /* 1 (default) = swap operands automatically when Cout % 128 == 0; 0 = never */
 void b200_debug_set_swap(int mode);
+void b200_debug_set_halo(int mode);   /* 1 = automatic halo-resident stride-1 3x3 conv (default), 0 = per-tap boxes */
+int b200_debug_last_path(void);       /* path of the last b200_conv2d_nhwc call: 1 = halo-resident, 0 = per-tap boxes */
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-pipeline post/pre-processing on the device.

@@ -14,6 +14,9 @@ import torch.nn.functional as F
 from diffusion_e2e_ft_b200 import ops
 
 DEV = "cuda"
+import os as _os
+if _os.environ.get("B200_DEBUG_FLAGS"):            # perf / bring-up experiments (tools/): never set in the test suite
+    ops._lib.load().b200_debug_set_flags(int(_os.environ["B200_DEBUG_FLAGS"]))
 
 
 def rel_l2(a, b):
@@ -157,6 +160,49 @@ def check_swap_epilogue_twins(seed=51):
     ref2 = (a.float() @ w2.float().t() + b2) * gate.float()
     e4 = rel_l2(o2, ref2)
     return max(e1 / 3e-5, e2 / 1e-7 if e2 > 0 else 0.0, e3 / 1e-5, e4 / 1e-3) * 1e-3, 1e-3
+
+
+def check_conv_halo(NB=2, H=40, W=64, Cin=128, Cout=128, shortcut=0, residual=False, out_f32=False, rowvec=False,
+                    stats=False, seed=71):
+    """Halo-resident stride-1 3x3 conv (one patch load per 64-channel block, nine taps as row-shifted UMMA views) vs
+    torch AND vs the per-tap-box path of the same kernel; asserts that the halo path was really taken."""
+    L = ops._lib.load()
+    x = _rand(NB, H, W, Cin, seed=seed)
+    w = _rand(Cout, Cin, 3, 3, seed=seed + 1, scale=1.0 / math.sqrt(9 * Cin))
+    b = _rand(Cout, seed=seed + 2, dtype=torch.float32)
+    ref = _conv_ref(x, w, b, 1, "same")
+    x2 = ws = None
+    if shortcut:
+        x2 = _rand(NB, H, W, shortcut, seed=seed + 4)
+        ws = _rand(Cout, shortcut, 1, 1, seed=seed + 5, scale=1.0 / math.sqrt(shortcut))
+        ref = ref + F.conv2d(x2.float().permute(0, 3, 1, 2), ws.float())
+    rv = None
+    if rowvec:
+        rv = _rand(NB, Cout, seed=seed + 6, dtype=torch.float32)
+        ref = ref + rv[:, :, None, None]
+    odt = torch.float32 if out_f32 else torch.float16
+    res = None
+    if residual:
+        res = _rand(NB, H, W, Cout, seed=seed + 7, dtype=odt)
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    wp = ops.pack_conv(w, ws)
+    outs = []
+    for halo in (1, 0):
+        L.b200_debug_set_halo(halo)
+        try:
+            o = ops.conv2d(x, wp, Cout, bias=b, x2=x2, rowvec=rv, residual=res, out_dtype=odt, stats=True if stats else None)
+            torch.cuda.synchronize()
+            assert L.b200_debug_last_path() == halo, f"expected conv path {halo}, kernel took {L.b200_debug_last_path()}"
+        finally:
+            L.b200_debug_set_halo(1)
+        outs.append(o)
+    e_ref = rel_l2(outs[0].permute(0, 3, 1, 2), ref)
+    e_tap = rel_l2(outs[0], outs[1])                       # same products, different summation order: fp32 / fp16 rounding
+    tol = 3e-5 if out_f32 else 1e-3
+    worst = max(e_ref, e_tap)
+    if stats:
+        worst = max(worst, rel_l2(outs[0]._cs.float(), outs[1]._cs.float()) * (tol / 1e-5))
+    return worst, tol
 
 
 def check_upsample_conv_phases(NB=2, H=12, W=10, C=128, seed=21):
@@ -569,6 +615,11 @@ CHECKS = {
     "conv_swap_768": lambda: check_conv(NB=1, H=96, W=768, Cin=128, Cout=128, seed=9),
     "conv_swap_1280_12": lambda: check_conv(NB=2, H=12, W=12, Cin=256, Cout=1280),
     "swap_epilogue_twins_stats": check_swap_epilogue_twins,
+    "conv_halo_128": lambda: check_conv_halo(),
+    "conv_halo_res_f32_stats": lambda: check_conv_halo(H=48, W=96, Cin=64, Cout=256, residual=True, out_f32=True, rowvec=True, stats=True),
+    "conv_halo_shortcut_320": lambda: check_conv_halo(NB=1, H=48, W=48, Cin=192, Cout=320, shortcut=128, out_f32=True),
+    "conv_halo_edges_768": lambda: check_conv_halo(NB=1, H=35, W=768, Cin=64, Cout=128, seed=73),
+    "conv_halo_ragged": lambda: check_conv_halo(NB=2, H=21, W=120, Cin=64, Cout=128, residual=True, seed=75),
     "conv_noswap_256": _noswap(lambda: check_conv(H=24, W=24, Cin=128, Cout=256, residual=True, out_f32=True)),
     "linear_noswap_1280": _noswap(lambda: check_linear(M=2000, N=1280, K=1280, residual=True, seed=2)),
     "linear_swap_small_m": lambda: check_linear(M=8, N=1280, K=1280, act=ops.ACT_SILU),
