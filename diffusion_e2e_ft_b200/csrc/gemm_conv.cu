@@ -149,27 +149,28 @@ static int g_swap_mode = 1;   // 1 = automatic (swap operands when Cout % 128 ==
 static int g_halo_mode = 1;   // 1 = automatic (halo-resident patch for stride-1 3x3 convs), 0 = never
 static int g_last_path = 0;   // 0 = per-tap boxes / GEMM, 1 = halo-resident conv (tests assert the path they mean to cover)
 
-// Tile geometry of the halo-resident conv: bh rows x bw columns of output pixels, one MMA (N = bw) per row and k-step.
-// bw % 16 == 0 (UMMA N granularity at M = 128), bw * bh <= 256 accumulator columns, (bw+2)(bh+2) <= kHaloMaxPatchPix.
+// Tile geometry of the halo-resident conv: bh rows x bw columns of output pixels.  The per-tap MMA covers
+// N = round_up16((bw + 2) * bh) consecutive patch pixels (<= 256 accumulator columns), of which bw * bh are real outputs;
+// the patch ((bh + 2) rows of bw + 2 pixels, plus the tail the last taps read past it) must fit kHaloMaxPatchPix rows.
 static bool pick_halo_tile(int Ho, int Wo, int* bw_out, int* bh_out) {
   double best = 0.0;
   int bbw = 0, bbh = 0;
-  const int cands[7] = {128, 112, 96, 80, 64, 48, 32};
-  for (int ci = 0; ci < 7; ++ci) {
-    const int bw = cands[ci];
-    if (bw > ((Wo + 15) / 16) * 16) continue;
-    for (int bh = 1; bh <= 8; ++bh) {
-      if (bw * bh > 256 || (bw + 2) * (bh + 2) > kHaloMaxPatchPix || bh > Ho) continue;
+  for (int bw = 8; bw <= 254 && bw <= Wo; ++bw) {
+    for (int bh = 1; bh <= 32 && bh <= Ho; ++bh) {
+      const int pitch = bw + 2;
+      const int n = (pitch * bh + 15) / 16 * 16;
+      if (n > 256) break;
+      if ((bh + 2) * pitch + (n - pitch * bh) + 2 > kHaloMaxPatchPix) continue;
       const double ew = (double)Wo / ((double)((Wo + bw - 1) / bw) * bw);
       const double eh = (double)Ho / ((double)((Ho + bh - 1) / bh) * bh);
-      double score = ew * eh * (0.75 + 0.25 * (bw * bh) / 256.0);       // mild preference for full tiles
-      if (bw < 64) score *= (bw == 48 ? 0.93 : 0.85);                   // short MMAs (N < 64) are issue-bound
-      score *= 1.0 - 0.02 * ((double)(bw + 2) * (bh + 2) / (bw * bh) - 1.0);   // halo traffic
+      double score = ew * eh * (double)(bw * bh) / n;                     // useful fraction of the MMA columns
+      score *= 0.9 + 0.1 * n / 256.0;                                     // fewer, fuller tiles
+      score *= 1.0 - 0.03 * ((double)(bw + 2) * (bh + 2) / (bw * bh) - 1.0);   // halo traffic
       if (score > best + 1e-9) { best = score; bbw = bw; bbh = bh; }
     }
   }
   *bw_out = bbw; *bh_out = bbh;
-  return bbw != 0 && best >= 0.80;
+  return bbw != 0 && best >= 0.78;
 }
 
 }  // namespace b200
@@ -336,8 +337,10 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
     bool taps_ok = num_taps == 9 && stride == 1 && out_mul == 1 && Ho == H && Wo == W;
     for (int i = 0; i < 9 && taps_ok; ++i) taps_ok = tap_dy[i] == i / 3 - 1 && tap_dx[i] == i % 3 - 1;
     int hbw = 0, hbh = 0;
-    if (can_swap && g_halo_mode && taps_ok && !g_force_bn && Wo >= 32 && pick_halo_tile(Ho, Wo, &hbw, &hbh)) {
+    if (can_swap && g_halo_mode && taps_ok && !g_force_bn && pick_halo_tile(Ho, Wo, &hbw, &hbh)) {
       p.bw = hbw; p.bh = hbh;
+      p.col_pitch = hbw + 2;
+      p.halo_n = ((hbw + 2) * hbh + 15) / 16 * 16;
       p.tiles_w = (Wo + hbw - 1) / hbw;
       p.tiles_h = (Ho + hbh - 1) / hbh;
       p.m_tiles = NB * p.tiles_w * p.tiles_h;
@@ -414,6 +417,7 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
     B200_CHECK_ARG(swap || bn_norm != 0, "b200_conv2d_nhwc: no tile shape (forced %d)", g_force_bn);
   }
   pick_patch(Ho, Wo, stride, pix, &p.bw, &p.bh);
+  p.col_pitch = p.bw;
   p.tiles_w = (Wo + p.bw - 1) / p.bw;
   p.tiles_h = (Ho + p.bh - 1) / p.bh;
   p.m_tiles = NB * p.tiles_w * p.tiles_h;

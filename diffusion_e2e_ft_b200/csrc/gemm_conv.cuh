@@ -41,6 +41,9 @@ struct GemmParams {
   int conv;
   int Ho, Wo;                  // conv-output grid the M tiles walk over
   int bw, bh, tiles_w, tiles_h;
+  int col_pitch;               // accumulator column q of a conv tile = pixel (q / col_pitch, q % col_pitch): bw normally,
+                               // bw + 2 in halo mode (the two halo columns of every patch row ride along as dead columns)
+  int halo_n;                  // halo mode: N of the per-tap MMA = round_up16((bw + 2) * bh)
   int cin_blocks, num_taps, in_stride;
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
   int k2_blocks;               // trailing k-blocks read from A2 (1x1 shortcut)
@@ -315,7 +318,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int ws = 0, pb = 0, acc = 0;
         uint32_t wphase = 0, pphase = 0, acc_phase = 0;
         const uint32_t a_base = smem_u32(smem_a), patch_base = smem_u32(smem_b);
-        const uint32_t idesc_row = make_idesc_f16(kBlockM, (uint32_t)p.bw, 0, 0);      // one MMA = one output row of bw pixels
+        // One MMA per (tap, k-step): its N = halo_n accumulator columns are halo_n CONSECUTIVE patch pixels starting at
+        // (dy, dx), i.e. bh output rows of bw pixels with the two halo pixels of every patch row riding along as dead
+        // columns (masked in the epilogue).  N stays large (A = the 128 x 16 weight slice is fetched once per 208-256
+        // columns; with one MMA per output row, N = 64, the A re-reads made the kernel smem-bound: 730 vs 1047 TFLOP/s).
+        const uint32_t idesc_tap = make_idesc_f16(kBlockM, (uint32_t)p.halo_n, 0, 0);
         const int pitch = p.bw + 2;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -333,18 +340,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mbar_wait(&full_bar[ws], wphase);
               tc_fence_after();
               const uint64_t adesc = make_desc_sw128(a_base + ws * S::kABytes, 16, 1024);
-              for (int r = 0; r < p.bh; ++r) {
-                // B operand rows = patch pixels ((r+dy)*pitch + dx) ... + bw: a 128-byte-granular start inside the
-                // SWIZZLE_128B tile; the descriptor's base-offset field carries (start >> 7) & 7 (tools/micro/
-                // umma_rowoffset_test.cu)
-                const uint32_t baddr = pbase + (uint32_t)(((r + dy) * pitch + dx) * 128);
-                uint64_t bdesc = make_desc_sw128(baddr, 16, 1024);
-                if (!(p.debug & 32)) bdesc |= (uint64_t)((baddr >> 7) & 7) << 49;
+              // B rows = patch pixels (dy * pitch + dx) ...: a 128-byte-granular start inside the SWIZZLE_128B tile.  The
+              // swizzle is a function of the absolute smem address, so the descriptor needs NO base offset
+              // (tools/micro/umma_rowoffset_test.cu on a B200: base-offset field 0 reads the named rows, (addr >> 7) & 7
+              // does not).
+              const uint64_t bdesc = make_desc_sw128(pbase + (uint32_t)((dy * pitch + dx) * 128), 16, 1024);
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                  if (!(p.debug & 8))
-                    umma_f16(d_tmem + r * p.bw, adesc + 2 * k, bdesc + 2 * k, idesc_row, (blk | t | k) != 0);
-              }
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                if (!(p.debug & 8)) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_tap, (blk | t | k) != 0);
               umma_commit(&empty_bar[ws]);
               if (++ws == kStages) { ws = 0; wphase ^= 1; }
             }
@@ -422,10 +425,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           bool ok;
           long long orow;
           if (p.conv) {
-            const int dh = pi / p.bw;
-            const int dw = pi - dh * p.bw;
+            const int dh = pi / p.col_pitch;
+            const int dw = pi - dh * p.col_pitch;
             const int ho = th * p.bh + dh, wo = tw * p.bw + dw;
-            ok = (dh < p.bh) && (ho < p.Ho) && (wo < p.Wo);
+            ok = (dh < p.bh) && (dw < p.bw) && (ho < p.Ho) && (wo < p.Wo);
             orow = ((long long)img * p.OH + (ho * p.out_mul + p.out_oy)) * p.OW + (wo * p.out_mul + p.out_ox);
           } else {
             const long long r = (long long)m_blk * BLOCK_N + pi;
@@ -481,7 +484,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t t_row = tmem_base + acc * kAccStrideCols + ((uint32_t)(quad * 32) << 16);
           // conv tiles may use fewer than BLOCK_N accumulator columns (bw * bh pixels)
-          const int ncols = p.conv ? min(BLOCK_N, (p.bw * p.bh + 31) & ~31) : BLOCK_N;
+          const int ncols = p.conv ? min(BLOCK_N, (p.col_pitch * p.bh + 31) & ~31) : BLOCK_N;
           if (!(p.debug & 16)) {
 #pragma unroll 1
             for (int c = eg * 32; c < ncols; c += 64) {
