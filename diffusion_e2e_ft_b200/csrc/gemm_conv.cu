@@ -97,6 +97,9 @@ static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtenso
   }
   int tiles = p.batch * p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
+  // fused statistics are carried across a CTA's tiles while (image, channel tile) stays the same: with the channel tile
+  // fastest in the tile index, a grid that is a multiple of n_tiles keeps every CTA on ONE channel tile
+  if (SWAP && p.chan_stats && p.n_tiles > 1 && grid > p.n_tiles) grid -= grid % p.n_tiles;
   kern<<<grid, kGemmThreads, S::kTotalBytes, st>>>(a, a2, b, p);
   B200_CHECK_LAUNCH("gemm_conv_kernel");
   return 0;

@@ -238,9 +238,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int blk = 0; blk < p.cin_blocks + p.k2_blocks; ++blk) {
             const bool main = blk < p.cin_blocks;
             mbar_wait(&patch_empty[pb], pphase ^ 1);
-            mbar_arrive_expect_tx(&patch_full[pb], patch_bytes);
+            mbar_arrive_expect_tx(&patch_full[pb], (p.debug & 2) ? 0u : patch_bytes);
             // one box = the whole (bh+2) x (bw+2) halo patch of this 64-channel block; image borders = OOB zero fill
-            if (main)
+            if (p.debug & 2) {
+            } else if (main)
               tma_load_4d(&tmA, &patch_full[pb], smem_b + pb * kHaloPatchBytes, blk * kBlockK, w0 - 1, h0 - 1, img,
                           kEvictNormal);
             else
@@ -250,8 +251,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int t = 0; t < ntaps; ++t) {
               const int kcol = main ? (t * p.cin_blocks + blk) : (9 * p.cin_blocks + (blk - p.cin_blocks));
               mbar_wait(&empty_bar[ws], wphase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[ws], (uint32_t)S::kABytes);
-              tma_load_3d(&tmB, &full_bar[ws], smem_a + ws * S::kABytes, kcol * kBlockK, n_blk * kBlockM, 0, kEvictLast);
+              mbar_arrive_expect_tx(&full_bar[ws], (p.debug & 4) ? 0u : (uint32_t)S::kABytes);
+              if (!(p.debug & 4))
+                tma_load_3d(&tmB, &full_bar[ws], smem_a + ws * S::kABytes, kcol * kBlockK, n_blk * kBlockM, 0, kEvictLast);
               if (++ws == kStages) { ws = 0; wphase ^= 1; }
             }
             pb ^= 1;
@@ -406,6 +408,40 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int et = threadIdx.x - 64;                             // 0..127 within the epilogue warps
       int acc = 0;
       uint32_t acc_phase = 0;
+      // Fused GroupNorm statistics of the vectorised path: per-lane shifted partial sums of this lane's four channels,
+      // carried ACROSS the tiles this persistent CTA processes for the same (image, channel tile) and merged into the
+      // global fp64 accumulators only when that key changes.  One atomic per tile and channel — tens of thousands of
+      // tiles hammering the same 2 x Cout addresses of an image — cost 0.3 ms per launch on the 768^2 convs
+      // (profiles/conv_stats_atomics_r02.txt); a CTA sees ~17 consecutive tiles of an image, so this is ~17x fewer.
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+      int scnt = 0;
+      long long skey = -1;                                         // (image * N + first channel) the sums belong to
+      auto flush_stats = [&]() {
+        // plain sums in fp64 (each lane has its own shift), folded over the four lanes that share a channel quad
+        double d1[4], d2[4];
+        const double n = (double)scnt;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double shd = (double)sh[k], a = (double)s1[k];
+          d1[k] = a + n * shd;
+          d2[k] = (double)s2[k] + 2.0 * shd * a + n * shd * shd;
+          d1[k] += __shfl_xor_sync(0xffffffffu, d1[k], 8);
+          d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], 8);
+          d1[k] += __shfl_xor_sync(0xffffffffu, d1[k], 16);
+          d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], 16);
+        }
+        if ((lane >> 3) == 0 && skey >= 0) {
+          double* dst = p.chan_stats + skey * 2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            atomicAdd(dst + 2 * k, d1[k]);
+            atomicAdd(dst + 2 * k + 1, d2[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s1[k] = s2[k] = sh[k] = 0.f;
+        scnt = 0;
+      };
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_blk = tile % p.n_tiles;                        // channel tile
         int rest = tile / p.n_tiles;
@@ -478,8 +514,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const OutT* __restrict__ res_q = res ? res + (long long)b * p.res_batch_stride + chq : nullptr;
           __half* __restrict__ out2_q = p.out2 ? p.out2 + (long long)b * p.out_batch_stride + chq : nullptr;
           using Vec = typename std::conditional<std::is_same<OutT, float>::value, float4, uint2>::type;
-          float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-          int scnt = 0;
+          if (p.chan_stats) {
+            // warp-uniform: every lane of the warp switches key on the same tile (invalid channel quads keep key -1)
+            const long long key_w = (long long)img * p.N + n_blk * kBlockM + quad * 32;
+            const long long key = cq_ok ? key_w + 4 * q : -1;
+            const long long cur_w = __shfl_sync(0xffffffffu, skey >= 0 ? skey - 4 * q : -1, 0);
+            if (cur_w != key_w && __any_sync(0xffffffffu, scnt > 0)) flush_stats();
+            skey = key;
+          }
           mbar_wait(&tmem_full[acc], acc_phase);
           tc_fence_after();
           const uint32_t t_row = tmem_base + acc * kAccStrideCols + ((uint32_t)(quad * 32) << 16);
@@ -565,29 +607,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
               __syncwarp();                          // the tile is rewritten by the next chunk
-            }
-          }
-          if (p.chan_stats) {
-            // plain sums in fp64 (each lane has its own shift), folded over the four lanes that share a channel quad
-            double d1[4], d2[4];
-            const double n = (double)scnt;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const double shd = (double)sh[k], a = (double)s1[k];
-              d1[k] = a + n * shd;
-              d2[k] = (double)s2[k] + 2.0 * shd * a + n * shd * shd;
-              d1[k] += __shfl_xor_sync(0xffffffffu, d1[k], 8);
-              d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], 8);
-              d1[k] += __shfl_xor_sync(0xffffffffu, d1[k], 16);
-              d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], 16);
-            }
-            if (pr == 0 && cq_ok) {
-              double* dst = p.chan_stats + ((long long)img * p.N + chq) * 2;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                atomicAdd(dst + 2 * k, d1[k]);
-                atomicAdd(dst + 2 * k + 1, d2[k]);
-              }
             }
           }
           tc_fence_before();
@@ -686,6 +705,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
+      if (p.chan_stats && p.vec_ok && __any_sync(0xffffffffu, scnt > 0)) flush_stats();
     } else {
     float (*stg)[33] = reinterpret_cast<float (*)[33]>(stage_smem + ew * (32 * 33 * 4));
     // per-warp row tables (16-byte aligned): element offsets of each of the warp's 32 rows relative to the

@@ -14,16 +14,19 @@ if len(sys.argv) > 4:
     _l.load().b200_debug_force_block_n(int(sys.argv[4]))
 if len(sys.argv) > 5:
     _l.load().b200_debug_set_swap(int(sys.argv[5]))
+if os.environ.get("B200_HALO"):
+    _l.load().b200_debug_set_halo(int(os.environ["B200_HALO"]))
 dev = "cuda"
 g = torch.Generator(device="cpu").manual_seed(0)
 r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).half().to(dev)
 if what.startswith("conv"):
-    cfg = {"conv128": (4, 768, 768, 128, 128), "conv256": (8, 384, 384, 256, 256), "conv512": (8, 192, 192, 512, 512),
+    cfg = {"conv128": (4, 768, 768, 128, 128), "conv128n8": (8, 768, 768, 128, 128), "conv128n2": (2, 768, 768, 128, 128), "conv256": (8, 384, 384, 256, 256), "conv512": (8, 192, 192, 512, 512),
            "conv320": (8, 96, 96, 320, 320), "conv640": (8, 48, 48, 640, 640), "conv1280": (8, 24, 24, 1280, 1280),
            "conv1280s": (8, 12, 12, 1280, 1280), "conv2560": (8, 24, 24, 2560, 1280)}[what]
     NB, H, W, Cin, Cout = cfg
     x = r(NB, H, W, Cin); w = ops.pack_conv(r(Cout, Cin, 3, 3, sc=1 / math.sqrt(9 * Cin))); b = torch.zeros(Cout, device=dev)
-    fn = lambda: ops.conv2d(x, w, Cout, bias=b)
+    st = True if os.environ.get("B200_STATS") else None
+    fn = lambda: ops.conv2d(x, w, Cout, bias=b, stats=st)
     flops = 2 * NB * H * W * Cout * 9 * Cin
 elif what.startswith("res"):          # res16 / res32: 128->128 768^2 conv with residual, fp16 / fp32 stream
     NB, H, W, Cin, Cout = 4, 768, 768, 128, 128
