@@ -340,7 +340,12 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
     bool taps_ok = num_taps == 9 && stride == 1 && out_mul == 1 && Ho == H && Wo == W;
     for (int i = 0; i < 9 && taps_ok; ++i) taps_ok = tap_dy[i] == i / 3 - 1 && tap_dx[i] == i % 3 - 1;
     int hbw = 0, hbh = 0;
-    if (can_swap && g_halo_mode && taps_ok && !g_force_bn && pick_halo_tile(Ho, Wo, &hbw, &hbh)) {
+    // epilogue-bound launches (fp32 output + fp32 residual over a short K = 9 * Cin <= 1152: 8 B read + 4-6 B written per
+    // output element against ~1 us of MMA per tile) gain nothing from cheaper operand loads and lose ~10 % to the dead
+    // halo columns their epilogue still walks: r2 bench, 128->128 768^2 fp32: 740 (halo) vs 825 TFLOP/s (per-tap boxes)
+    const bool epi_bound = out_f32 && residual && Cin <= 128 && !X2;
+    if (can_swap && g_halo_mode && taps_ok && !g_force_bn && (!epi_bound || g_halo_mode == 2) &&
+        pick_halo_tile(Ho, Wo, &hbw, &hbh)) {
       p.bw = hbw; p.bh = hbh;
       p.col_pitch = hbw + 2;
       p.halo_n = ((hbw + 2) * hbh + 15) / 16 * 16;
