@@ -107,10 +107,14 @@ class FlatTrainer:
     middle of a window.  Data parallel (one process per GPU, `torch.distributed` initialised): the flat gradient is cut
     into buckets of `bucket_mb` in gradient-ready order — the parameters whose gradients only arrive at the very end
     of backward (every resnet's `time_emb_proj` and the time / class embedding MLPs, produced by the embedding block
-    that runs first in forward) get their own bucket, so they do not hold the others back; a bucket's SUM all-reduce is
-    launched asynchronously (NCCL stream) the moment autograd has accumulated its last parameter, i.e. it overlaps the
-    rest of the backward pass as accelerate's DDP does for the reference.  The 1/world_size of the average is folded
-    into the optimizer kernel's gradient multiplier (no extra pass over the 3.46 GB buffer).
+    that runs first in forward) get their own bucket, so they do not hold the others back.  With `overlap=True` a
+    bucket's SUM all-reduce is launched asynchronously (NCCL stream) the moment autograd has accumulated its last
+    parameter, as accelerate's DDP does for the reference; the DEFAULT is `overlap=False` — all buckets are reduced in
+    `step()` after backward — because on this engine overlap is a loss: the GEMM / conv kernels are persistent with one
+    200 KB-smem CTA per SM, so while NCCL's channel CTAs occupy SMs a 148-CTA grid no longer fits in one wave and the
+    backward kernels take two (measured on 2 x B200, bs 2 768^2: 515 ms / step with overlap vs 260 ms without, against
+    5.7 ms for the 3.46 GB all-reduce alone at 604 GB/s bus bandwidth: profiles/bench_r02_n2.json).  The 1/world_size
+    of the average is folded into the optimizer kernel's gradient multiplier (no extra pass over the 3.46 GB buffer).
 
     Mixed precision: backward GEMM operands are fp16, so the loss is multiplied by a loss scale held ON THE DEVICE
     (`state[0]`); the fused optimizer kernel skips the step and halves the scale when the gradient norm is non-finite,
@@ -120,7 +124,7 @@ class FlatTrainer:
     LATE_GRAD_KEYS = ("time_emb_proj", "time_embedding", "class_embedding")
 
     def __init__(self, module, lr=3e-5, weight_decay=1e-2, max_grad_norm=1.0, accumulation_steps=1, group=None,
-                 loss_scale=LOSS_SCALE, bucket_mb=256, dynamic_loss_scale=True, growth_interval=2000, overlap=True):
+                 loss_scale=LOSS_SCALE, bucket_mb=256, dynamic_loss_scale=True, growth_interval=2000, overlap=False):
         import torch.distributed as dist
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         if not named:
