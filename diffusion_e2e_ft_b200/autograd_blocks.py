@@ -609,11 +609,10 @@ class _VAEAttentionFn(torch.autograd.Function):
             ops.linear(do[b], v[b], out=dp[:, :L], out_dtype=F32)
             ds = ops.softmax_bwd_rows(p_buf[b], dp, scale, cols=L)                     # [L, Lp] fp16, padding 0
             del dp
-            ops.linear(ds, ops.transpose_rows(k_b), out=dqk[b, :, :C])                 # K^T [C, L8], L8 == Lp
-            dst = ops.transpose_rows(ds[:, :L])                                         # [L, L8]
-            ops.linear(dst, ops.transpose_rows(q_b), out=dqk[b, :, C:])
-            pt = ops.transpose_rows(p_buf[b][:, :L])
-            ops.linear(pt, ops.transpose_rows(do[b]), out=dv[b])
+            # dQ = dS K, dK = dS^T Q, dV = P^T dO with the row-major operands consumed MN-major as stored (no transposes)
+            ops.linear(ds[:, :L], k_b, out=dqk[b, :, :C], w_t=True)
+            ops.linear(ds[:, :L], q_b, out=dqk[b, :, C:], a_t=True, w_t=True)
+            ops.linear(p_buf[b][:, :L], do[b], out=dv[b], a_t=True, w_t=True)
         dhn, _, _ = bw.linear_bwd(hn.view(B * L, C), pk["wqk"], dqk.view(B * L, 2 * C), need_dw=False)
         dhn, _, _ = bw.linear_bwd(hn.view(B * L, C), pk["wv"], dv.view(B * L, C), need_dw=False, da_add=dhn)
         (dx,), _, _ = ops.group_norm_bwd([x], dhn.view(B, H, W, C), mr, pk["g"], pk["b"], m.groups, False, [dout], F32)

@@ -25,15 +25,38 @@ def linear_bwd(a, w, dy, need_da=True, da_dtype=F16, da_add=None, need_dw=True, 
     assert dy.shape == (M, N) and N % 8 == 0 and K % 8 == 0
     da = dw = db = None
     if need_da:
-        wt = ops.transpose_rows(w)                                       # [K, N]
-        da = ops.linear(dy, wt, residual=da_add, out_dtype=da_dtype)
+        # da = dy @ w: w [N, K] IS the [contraction, out-column] matrix -> MN-major B operand, no W^T copy
+        da = ops.linear(dy, w, residual=da_add, out_dtype=da_dtype, w_t=True)
     if need_dw:
-        dyt = ops.transpose_rows(dy)                                     # [N, ru8(M)]
-        at = ops.transpose_rows(a)                                       # [K, ru8(M)]
-        dw = ops.linear(dyt, at, out_dtype=F32)
+        # dw = dy^T @ a: both operands are stored [contraction = M rows][columns] -> MN-major A and B, no transposes.
+        # An [N x K] output is only a handful of 128 x 256 tiles: split the row contraction over `S` batches (views of
+        # the same buffers) so the GEMM fills the 148 SMs, then fold the partial sums.
+        S = _row_splits(M, N, K)
+        if S > 1 and dy.stride(1) == 1 and a.stride(1) == 1:
+            mc = M // S
+            dy3 = dy.as_strided((S, mc, N), (mc * dy.stride(0), dy.stride(0), 1), dy.storage_offset())
+            a3 = a.as_strided((S, mc, K), (mc * a.stride(0), a.stride(0), 1), a.storage_offset())
+            part = ops.linear(dy3, a3, out_dtype=F32, a_t=True, w_t=True)            # [S, N, K]
+            dw = ops.col_sum(part.view(S, N * K)).view(N, K)
+        else:
+            dw = ops.linear(dy, a, out_dtype=F32, a_t=True, w_t=True)
         if bias:
             db = ops.col_sum(dy)
     return da, dw, db
+
+
+def _row_splits(M, N, K, target_ctas=296, min_rows=512):
+    """Number of equal row chunks (a divisor of M / 64) for a split-K weight-gradient GEMM of an [N x K] output."""
+    if M % 64 != 0:
+        return 1
+    tiles = ((N + 127) // 128) * ((K + 255) // 256)
+    want = max(1, min(target_ctas // max(tiles, 1), M // min_rows))
+    kb = M // 64
+    best = 1
+    for s in range(1, want + 1):
+        if kb % s == 0:
+            best = s
+    return best
 
 
 # -------------------------------------------------------------------------------------------------- conv
@@ -190,15 +213,6 @@ def attention_bwd(q, k, v, do, heads, scale, outs=None):
     def heads_view(t2d):                      # [L, heads*64] -> [heads, L, 64] strided view
         return t2d.unflatten(-1, (heads, 64)).permute(1, 0, 2)
 
-    def transpose_per_head(m):                # [heads, T, Tkp] -> [heads, Tkp, T8] (zero padded queries)
-        if T == T8:                           # one launch: [Tkp, heads*T], head h = columns h*T .. (h+1)*T
-            t = ops.gather_planar(m.view(heads, 1, T, Tkp))
-            return t.as_strided((heads, Tkp, T), (T, t.stride(0), 1))
-        t = torch.empty((heads, Tkp, T8), dtype=F16, device=dev)
-        for h in range(heads):
-            ops.gather_planar(m[h].view(1, 1, T, Tkp), out=t[h])
-        return t
-
     for b in range(B):
         qh, kh, vh, doh = heads_view(q[b]), heads_view(k[b]), heads_view(v[b]), heads_view(do[b])
         s = torch.zeros((heads, T, Tkp), dtype=F32, device=dev)
@@ -208,12 +222,11 @@ def attention_bwd(q, k, v, do, heads, scale, outs=None):
         ops.linear(doh, vh, out=dp[:, :, :Tk], out_dtype=F32)
         ds = ops.softmax_bwd_rows(p, dp, scale, cols=Tk)                 # [heads, T, Tkp] fp16, padding 0
         del s, dp
-        # dQ[h] = dS[h] @ K[h]: contraction over keys -> K^T [64, Tkp] per head
-        kt = ops.transpose_rows(k[b]).view(heads, 64, Tkp)
-        ops.linear(ds, kt, out=heads_view(dq[b]))
-        # dK[h] = dS[h]^T @ Q[h], dV[h] = P[h]^T @ dO[h]: contraction over queries (zero padded to T8)
-        qt = ops.transpose_rows(q[b]).view(heads, 64, T8)
-        dot = ops.transpose_rows(do[b]).view(heads, 64, T8)
-        ops.linear(transpose_per_head(ds)[:, :Tk], qt, out=heads_view(dk[b]))
-        ops.linear(transpose_per_head(p)[:, :Tk], dot, out=heads_view(dv[b]))
+        # The three products contract over rows of row-major tensors; the GEMM kernel consumes them MN-major as stored
+        # (round 1 transposed dS, P, Q, K, dO through `gather_planar`: 84 of 254 ms of a bs-2 768^2 iteration).
+        # dQ[h] = dS[h] @ K[h]            (K [Tk, 64] = [contraction, columns])
+        ops.linear(ds[:, :, :Tk], kh, out=heads_view(dq[b]), w_t=True)
+        # dK[h] = dS[h]^T @ Q[h], dV[h] = P[h]^T @ dO[h]   (contraction over the T query rows of both operands)
+        ops.linear(ds[:, :, :Tk], qh, out=heads_view(dk[b]), a_t=True, w_t=True)
+        ops.linear(p[:, :, :Tk], doh, out=heads_view(dv[b]), a_t=True, w_t=True)
     return dq, dk, dv

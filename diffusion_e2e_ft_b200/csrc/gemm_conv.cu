@@ -186,7 +186,7 @@ extern "C" void b200_debug_set_flags(int f) { b200::g_debug = f; }
 extern "C" void b200_debug_set_swap(int m) { b200::g_swap_mode = m; }
 extern "C" void b200_debug_set_halo(int m) { b200::g_halo_mode = m; }
 extern "C" int b200_debug_last_path(void) { return b200::g_last_path; }
-extern "C" int b200_abi_version(void) { return 2; }
+extern "C" int b200_abi_version(void) { return 3; }
 // Tile width used by the GEGLU epilogue for a packed width N (= 2 x output width); weights must be
 // packed per tile as [value half | gate half] with this width.
 extern "C" int b200_geglu_block_n(int N) {
@@ -198,8 +198,10 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
                            const float* bias, int bias_row, const void* residual, long long ld_res,
                            long long res_batch_stride, void* out, long long ldo,
                            long long out_batch_stride, int out_f32, int act, float alpha,
-                           double* chan_stats, int rows_per_img, void* out2_f16, int res_mul, void* stream) {
+                           double* chan_stats, int rows_per_img, void* out2_f16, int res_mul, int a_mn, int w_mn,
+                           void* stream) {
   B200_CHECK_ARG(A && W && out, "b200_linear: null pointer");
+  B200_CHECK_ARG(!(a_mn || w_mn) || act != ACT_GEGLU, "b200_linear: MN-major operands are not combined with GEGLU");
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "b200_linear: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
   B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "b200_linear: lda/ldw must be multiples of 8 elements (16 B)");
   B200_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
@@ -235,6 +237,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
     const bool normal_ok = !chan_stats || rows_per_img % kBlockM == 0;   // stats: a row tile stays inside one image
     for (int i = 0; i < 5 && normal_ok; ++i) {
       if (g_force_bn && nc[i] != g_force_bn) continue;
+      if (w_mn && nc[i] % 64 != 0) continue;                              // MN-major tiles are built from 64-row atoms
       double c = tiles_cost((long long)p.m_tiles * batch * ((N + nc[i] - 1) / nc[i]), nc[i]);
       if (c < best - 1e-9) { best = c; bn = nc[i]; swap = false; }
     }
@@ -243,6 +246,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
       for (int i = 0; i < 3; ++i) {
         if (g_force_bn && pc[i] != g_force_bn) continue;
         if (chan_stats && rows_per_img % pc[i] != 0) continue;
+        if (a_mn && pc[i] % 64 != 0) continue;
         double c = tiles_cost((long long)batch * ((M + pc[i] - 1) / pc[i]) * ((N + 127) / 128), pc[i]) * 0.85;  // cheaper epilogue, fewer barrier round trips
         if (c < best - 1e-9) { best = c; bn = pc[i]; swap = true; }
       }
@@ -260,6 +264,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.residual = residual; p.ld_res = ld_res; p.res_batch_stride = res_batch_stride; p.res_mul = res_mul;
   p.act = act; p.alpha = alpha; p.debug = g_debug;
   p.chan_stats = chan_stats; p.rows_per_img = rows_per_img; p.out2 = (__half*)out2_f16;
+  p.act_mn = a_mn; p.w_mn = w_mn;
   p.out_mul = 1;
   // swapped epilogue: 16-byte (fp32) / 8-byte (fp16) accesses over runs of 4 channels
   {
@@ -270,14 +275,26 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   }
 
   CUtensorMap ta, tb;
-  {
+  if (a_mn) {                 // A stored [K][M]: innermost dimension = rows (M), boxes of 64 rows x 64 k
+    uint64_t dims[3] = {(uint64_t)M, (uint64_t)K, (uint64_t)(p.a_batched ? batch : 1)};
+    uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(p.a_batched ? a_batch_stride : (long long)K * lda) * 2};
+    uint32_t box[3] = {64, kBlockK, 1};
+    int r = encode_tmap(&ta, A, 3, dims, str, box, nullptr);
+    if (r) return r;
+  } else {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(p.a_batched ? batch : 1)};
     uint64_t str[2] = {(uint64_t)lda * 2, (uint64_t)(p.a_batched ? a_batch_stride : (long long)M * lda) * 2};
     uint32_t box[3] = {kBlockK, (uint32_t)(swap ? bn : kBlockM), 1};
     int r = encode_tmap(&ta, A, 3, dims, str, box, nullptr);
     if (r) return r;
   }
-  {
+  if (w_mn) {                 // W stored [K][N]
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)K, (uint64_t)(p.b_batched ? batch : 1)};
+    uint64_t str[2] = {(uint64_t)ldw * 2, (uint64_t)(p.b_batched ? w_batch_stride : (long long)K * ldw) * 2};
+    uint32_t box[3] = {64, kBlockK, 1};
+    int r = encode_tmap(&tb, W, 3, dims, str, box, nullptr);
+    if (r) return r;
+  } else {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)(p.b_batched ? batch : 1)};
     uint64_t str[2] = {(uint64_t)ldw * 2, (uint64_t)(p.b_batched ? w_batch_stride : (long long)N * ldw) * 2};
     uint32_t box[3] = {kBlockK, (uint32_t)(swap ? kBlockM : bn), 1};

@@ -37,6 +37,10 @@ struct GemmParams {
   int M, N, num_k_blocks;
   int batch, m_tiles, n_tiles;
   int a_batched, b_batched;    // operand has a batch dimension (else shared across the batch)
+  int act_mn, w_mn;            // LINEAR: the activation / weight operand is stored [K][rows] (MN-major, e.g. dY for a weight
+                               // gradient dY^T X) and is fed to the MMA as is — no transposition pass.  smem layout per
+                               // stage: rows / 64 boxes of [64 k-rows][64 rows x 2 B], 8192 B apart (descriptor LBO 8192,
+                               // SBO 1024: tools/micro/umma_mnmajor_test.cu)
   // ---- conv geometry (conv != 0)
   int conv;
   int Ho, Wo;                  // conv-output grid the M tiles walk over
@@ -300,14 +304,27 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_4d(&tmA2, &full_bar[stage], s_act, (kb - tap_blocks) * kBlockK, w0, h0, img,
                             kEvictNormal);
               }
+            } else if (p.act_mn) {
+#pragma unroll 1
+              for (int j = 0; j < kActRows / 64; ++j)
+                tma_load_3d(&tmA, &full_bar[stage], (uint8_t*)s_act + j * 8192, m_blk * kActRows + j * 64, kb * kBlockK,
+                            p.a_batched ? b : 0, kEvictNormal);
             } else {
               tma_load_3d(&tmA, &full_bar[stage], s_act, kb * kBlockK, m_blk * kActRows, p.a_batched ? b : 0,
                           kEvictNormal);
             }
           }
-          if (!(p.debug & 4))
-            tma_load_3d(&tmB, &full_bar[stage], s_w, kb * kBlockK, n_blk * kWRows, p.b_batched ? b : 0,
-                        kEvictLast);
+          if (!(p.debug & 4)) {
+            if (p.w_mn) {
+#pragma unroll 1
+              for (int j = 0; j < kWRows / 64; ++j)
+                tma_load_3d(&tmB, &full_bar[stage], (uint8_t*)s_w + j * 8192, n_blk * kWRows + j * 64, kb * kBlockK,
+                            p.b_batched ? b : 0, kEvictLast);
+            } else {
+              tma_load_3d(&tmB, &full_bar[stage], s_w, kb * kBlockK, n_blk * kWRows, p.b_batched ? b : 0,
+                          kEvictLast);
+            }
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -368,6 +385,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+      // MMA operand A = weights when SWAP, activations otherwise; either may be MN-major (stored [K][rows])
+      const bool a_mn = SWAP ? (p.w_mn != 0) : (p.act_mn != 0);
+      const bool b_mn = SWAP ? (p.act_mn != 0) : (p.w_mn != 0);
+      const uint32_t idesc_rt = make_idesc_f16(kBlockM, BLOCK_N, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -375,12 +396,16 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_desc_sw128(a_base + stage * S::kABytes, 16, 1024);
-          const uint64_t bdesc = make_desc_sw128(b_base + stage * S::kBBytes, 16, 1024);
+          // K-major: rows of 128 B, k-step = +32 B inside the swizzle row.  MN-major: [k-row][64 rows] atoms 8192 B apart
+          // (LBO), 8-k-row groups 1024 B apart (SBO), k-step = 16 k-rows = +2048 B.
+          const uint64_t adesc = a_mn ? make_desc_sw128(a_base + stage * S::kABytes, 8192, 1024)
+                                      : make_desc_sw128(a_base + stage * S::kABytes, 16, 1024);
+          const uint64_t bdesc = b_mn ? make_desc_sw128(b_base + stage * S::kBBytes, 8192, 1024)
+                                      : make_desc_sw128(b_base + stage * S::kBBytes, 16, 1024);
+          const uint64_t astep = a_mn ? 128 : 2, bstep = b_mn ? 128 : 2;        // in 16-byte units
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 32 bytes (16 fp16) along K inside the 128B swizzle row: +2 in 16-byte units
-            if (!(p.debug & 8)) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (!(p.debug & 8)) umma_f16(d_tmem, adesc + astep * k, bdesc + bstep * k, idesc_rt, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);           // smem slot reusable once these MMAs retire
           if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);

@@ -134,18 +134,22 @@ def _new_stats(nb, c, device):
 
 @_timed("gemm_linear")
 def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE, alpha=1.0,
-           bias_row=False, stats_rows_per_img=0, f16_copy=False, res_mul=False):
+           bias_row=False, stats_rows_per_img=0, f16_copy=False, res_mul=False, a_t=False, w_t=False):
     """`stats_rows_per_img` > 0: also accumulate per-(image, channel) sum / sum-of-squares of the output
     (attached to the result as `._cs`) for a following GroupNorm.  `f16_copy`: an fp32 output also gets an
     fp16 twin (`._h16`) written by the same epilogue, so a following GEMM needs no cast pass."""
-    """a: [M,K] or [B,M,K] fp16 (last dim contiguous); w: [N,K] or [B,N,K] fp16."""
+    """a: [M,K] or [B,M,K] fp16 (last dim contiguous); w: [N,K] or [B,N,K] fp16.
+    `a_t` / `w_t`: the operand is given TRANSPOSED-AS-STORED — a: [K,M], w: [K,N] (row-major, last dim contiguous) —
+    and is consumed MN-major by the tensor core: out = a.T @ w (a_t, w_t), a @ w (w_t), a.T @ w.T (a_t).  This is how
+    the backward pass contracts over rows (weight gradients dY^T X, attention dS^T Q / P^T dO / dS K, data gradients
+    dY W) without transposition kernels."""
     _need_cuda(a, w)
     assert a.dtype == F16 and w.dtype == F16 and a.stride(-1) == 1 and w.stride(-1) == 1
     batched = a.dim() == 3 or w.dim() == 3
     B = (a.shape[0] if a.dim() == 3 else w.shape[0]) if batched else 1
-    M, K = a.shape[-2], a.shape[-1]
-    N = w.shape[-2]
-    assert w.shape[-1] == K
+    M, K = (a.shape[-1], a.shape[-2]) if a_t else (a.shape[-2], a.shape[-1])
+    N = w.shape[-1] if w_t else w.shape[-2]
+    assert (w.shape[-2] if w_t else w.shape[-1]) == K, (a.shape, w.shape, a_t, w_t)
     n_out = N // 2 if act == ACT_GEGLU else N
     if out is None:
         out = torch.empty((B, M, n_out) if batched else (M, n_out), dtype=out_dtype, device=a.device)
@@ -168,7 +172,8 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
         _p(residual), residual.stride(-2) if residual is not None else 0,
         (residual.stride(0) if (residual is not None and batched) else 0),
         _p(out), out.stride(-2), out.stride(0) if batched else 0, int(out.dtype == F32),
-        act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _p(h16), int(res_mul), _stream())
+        act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _p(h16), int(res_mul),
+        int(a_t), int(w_t), _stream())
     _lib.check(rc, "b200_linear")
     STATS.add("linear", 2 * B * M * N * K)
     if ev is not None:

@@ -54,6 +54,9 @@ int b200_linear(const void* A, long long lda, long long a_batch_stride,
                 int rows_per_img,
                 void* out2_f16 /* optional fp16 copy of `out` (same strides) for a following GEMM operand */,
                 int res_mul /* 1: out = act(alpha*acc + bias) * residual (GEGLU as gate GEMM + value GEMM) */,
+                int a_mn /* 1: A is stored [K][M] (row pitch lda >= M): out = A^T-as-stored x W^T without a transposition
+                            pass (MN-major UMMA operand).  Weight gradients dW = dY^T X, attention backward dK = dS^T Q */,
+                int w_mn /* 1: W is stored [K][N] (row pitch ldw >= N): data gradients dX = dY W, dQ = dS K */,
                 void* stream);
 
 /* GEGLU tile width for packed width N (weights/bias rows are interleaved per tile of this width:

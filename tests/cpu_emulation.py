@@ -39,7 +39,7 @@ def _act(r, act):
 
 
 def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ops.ACT_NONE, alpha=1.0, bias_row=False,
-           stats_rows_per_img=0, f16_copy=False, res_mul=False):
+           stats_rows_per_img=0, f16_copy=False, res_mul=False, a_t=False, w_t=False):
     assert a.stride(-1) == 1 and w.stride(-1) == 1 and a.dtype == F16 and w.dtype == F16
     assert a.stride(-2) % 8 == 0 and w.stride(-2) % 8 == 0, "TMA: 16-byte row pitch"
     assert a.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0, "TMA: 16-byte base"
@@ -48,7 +48,9 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ops.ACT_
     if w.dim() == 3:
         assert w.stride(0) % 8 == 0
     assert out is None or (out.data_ptr() % 16 == 0 and out.stride(-1) == 1)
-    r = a.float() @ w.float().transpose(-1, -2) * alpha
+    af = a.float().transpose(-1, -2) if a_t else a.float()
+    wf = w.float() if w_t else w.float().transpose(-1, -2)
+    r = af @ wf * alpha
     if bias is not None:
         r = r + (bias[:, None] if bias_row else bias)
     if residual is not None:

@@ -59,6 +59,31 @@ def check_linear(M=300, N=320, K=320, bias=True, residual=False, out_f32=False, 
     return err, tol
 
 
+def check_linear_mn(M=1000, N=320, K=200, a_t=False, w_t=False, batch=0, out_f32=True, swap=1, seed=81):
+    """MN-major operands: a given as [K, M] and / or w as [K, N] (row-major, as the backward pass finds them) are
+    consumed by the tensor core as stored — out = a^T w, a w, a^T w^T — against torch on the same fp16 values.
+    Row pitches are padded (row-strided views), M / N / K ragged against the 64-row atoms."""
+    bs = (batch,) if batch else ()
+    ar = _rand(*bs, M, K, seed=seed)                    # logical a [M, K]
+    wr = _rand(*bs, N, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
+    ref = torch.matmul(ar.float(), wr.float().transpose(-1, -2))
+
+    def stored(t, transposed):
+        t = t.transpose(-1, -2).contiguous() if transposed else t
+        pad = torch.zeros(*t.shape[:-1], (t.shape[-1] + 15) // 8 * 8, dtype=t.dtype, device=t.device)   # padded row pitch
+        pad[..., :t.shape[-1]] = t
+        return pad[..., :t.shape[-1]]
+    a, w = stored(ar, a_t), stored(wr, w_t)
+    L = ops._lib.load()
+    L.b200_debug_set_swap(swap)
+    try:
+        out = ops.linear(a, w, out_dtype=torch.float32 if out_f32 else torch.float16, a_t=a_t, w_t=w_t)
+        torch.cuda.synchronize()
+    finally:
+        L.b200_debug_set_swap(1)
+    return rel_l2(out, ref), (3e-5 if out_f32 else 1e-3)
+
+
 def check_geglu_two_gemm(M=300, C=320, seed=17):
     """GEGLU as gate GEMM (erf-GELU epilogue) + value GEMM with a multiplicative residual operand."""
     a = _rand(M, C, seed=seed)
@@ -624,6 +649,12 @@ CHECKS = {
     "linear_noswap_1280": _noswap(lambda: check_linear(M=2000, N=1280, K=1280, residual=True, seed=2)),
     "linear_swap_small_m": lambda: check_linear(M=8, N=1280, K=1280, act=ops.ACT_SILU),
     "linear_swap_ragged": lambda: check_linear(M=777, N=384, K=200, residual=True, out_f32=True),
+    "linear_mn_w": lambda: check_linear_mn(w_t=True),                                        # dX = dY W
+    "linear_mn_w_noswap": lambda: check_linear_mn(w_t=True, swap=0, N=64, K=1000, M=333),    # dQ = dS K (N = 64)
+    "linear_mn_aw": lambda: check_linear_mn(M=320, N=640, K=2304, a_t=True, w_t=True),       # dW = dY^T X
+    "linear_mn_aw_noswap": lambda: check_linear_mn(M=77, N=64, K=1000, a_t=True, w_t=True, swap=0),   # dK = dS^T Q, 77 keys
+    "linear_mn_a": lambda: check_linear_mn(M=200, N=256, K=520, a_t=True, out_f32=False),
+    "linear_mn_aw_batched": lambda: check_linear_mn(M=576, N=64, K=576, a_t=True, w_t=True, batch=5, swap=0),
     "gn_f16": lambda: check_group_norm(),
     "gn_f32_concat": lambda: check_group_norm(C1=1280, C2=640, in_f32=True),
     "gn_concat_f16_nosilu": lambda: check_group_norm(C1=640, C2=320, silu=False),
