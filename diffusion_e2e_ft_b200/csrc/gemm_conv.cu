@@ -354,13 +354,14 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
   const bool can_swap = g_swap_mode && Cout >= 128 && !out_nchw;
   // ---- halo-resident path: stride-1 "same" 3x3 convs in the swapped orientation
   {
-    bool taps_ok = num_taps == 9 && stride == 1 && out_mul == 1 && Ho == H && Wo == W;
-    for (int i = 0; i < 9 && taps_ok; ++i) taps_ok = tap_dy[i] == i / 3 - 1 && tap_dx[i] == i % 3 - 1;
+    bool taps_ok = stride == 1 && Ho == H && Wo == W && !(X2 && out_mul != 1);
+    for (int i = 0; i < num_taps && taps_ok; ++i)
+      taps_ok = tap_dy[i] >= -1 && tap_dy[i] <= 1 && tap_dx[i] >= -1 && tap_dx[i] <= 1;
     int hbw = 0, hbh = 0;
     // epilogue-bound launches (fp32 output + fp32 residual over a short K = 9 * Cin <= 1152: 8 B read + 4-6 B written per
     // output element against ~1 us of MMA per tile) gain nothing from cheaper operand loads and lose ~10 % to the dead
     // halo columns their epilogue still walks: r2 bench, 128->128 768^2 fp32: 740 (halo) vs 825 TFLOP/s (per-tap boxes)
-    const bool epi_bound = out_f32 && residual && Cin <= 128 && !X2;
+    const bool epi_bound = out_f32 && residual && num_taps * Cin <= 1152 && !X2;
     if (can_swap && g_halo_mode && taps_ok && !g_force_bn && (!epi_bound || g_halo_mode == 2) &&
         pick_halo_tile(Ho, Wo, &hbw, &hbh)) {
       p.bw = hbw; p.bh = hbh;
@@ -372,11 +373,12 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
       p.n_tiles = (Cout + 127) / 128;
       p.M = NB * Ho * Wo;
       p.cin_blocks = Cin / 64;
-      p.num_taps = 9;
+      p.num_taps = num_taps;
+      for (int i = 0; i < num_taps; ++i) { p.tap_dy[i] = tap_dy[i]; p.tap_dx[i] = tap_dx[i]; }
       p.in_stride = 1;
       p.k2_blocks = X2 ? C2 / 64 : 0;
-      p.num_k_blocks = 9 * p.cin_blocks + p.k2_blocks;
-      p.out_mul = 1; p.out_oy = 0; p.out_ox = 0; p.OH = Ho; p.OW = Wo;
+      p.num_k_blocks = num_taps * p.cin_blocks + p.k2_blocks;
+      p.out_mul = out_mul; p.out_oy = out_oy; p.out_ox = out_ox; p.OH = Ho * out_mul; p.OW = Wo * out_mul;
       p.out = out; p.ldo = Cout; p.out_f32 = out_f32; p.out_nchw = 0;
       p.bias = bias; p.rowvec = rowvec; p.ld_rowvec = ld_rowvec;
       p.residual = residual; p.ld_res = Cout;
@@ -401,7 +403,7 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
         if (r) return r;
       }
       {
-        const long long Kt = 9LL * Cin + (X2 ? C2 : 0);
+        const long long Kt = (long long)num_taps * Cin + (X2 ? C2 : 0);
         uint64_t dims[3] = {(uint64_t)Kt, (uint64_t)Cout, 1};
         uint64_t str[2] = {(uint64_t)Kt * 2, (uint64_t)Kt * Cout * 2};
         uint32_t box[3] = {kBlockK, (uint32_t)kBlockM, 1};

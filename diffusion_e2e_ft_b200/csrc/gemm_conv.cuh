@@ -251,9 +251,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else
               tma_load_4d(&tmA2, &patch_full[pb], smem_b + pb * kHaloPatchBytes, (blk - p.cin_blocks) * kBlockK, w0 - 1,
                           h0 - 1, img, kEvictNormal);
-            const int ntaps = main ? 9 : 1;                         // the 1x1 shortcut operand only feeds the centre tap
+            const int ntaps = main ? p.num_taps : 1;                // the 1x1 shortcut operand only feeds the centre tap
             for (int t = 0; t < ntaps; ++t) {
-              const int kcol = main ? (t * p.cin_blocks + blk) : (9 * p.cin_blocks + (blk - p.cin_blocks));
+              const int kcol = main ? (t * p.cin_blocks + blk) : (p.num_taps * p.cin_blocks + (blk - p.cin_blocks));
               mbar_wait(&empty_bar[ws], wphase ^ 1);
               mbar_arrive_expect_tx(&full_bar[ws], (p.debug & 4) ? 0u : (uint32_t)S::kABytes);
               if (!(p.debug & 4))
@@ -352,10 +352,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&patch_full[pb], pphase);
             tc_fence_after();
             const uint32_t pbase = patch_base + pb * kHaloPatchBytes;
-            const int ntaps = main ? 9 : 1;
+            const int ntaps = main ? p.num_taps : 1;
             for (int t = 0; t < ntaps; ++t) {
-              const int tap = main ? t : 4;
-              const int dy = tap / 3, dx = tap - 3 * dy;              // patch offsets (0..2): tap (dy-1, dx-1)
+              // patch offsets (0..2) of tap t: any tap set inside the 3x3 neighbourhood, in any order (forward convs,
+              // flipped-tap data gradients, the 2x2 phases of nearest-2x + conv)
+              const int dy = main ? p.tap_dy[t] + 1 : 1, dx = main ? p.tap_dx[t] + 1 : 1;
               mbar_wait(&full_bar[ws], wphase);
               tc_fence_after();
               const uint64_t adesc = make_desc_sw128(a_base + ws * S::kABytes, 16, 1024);

@@ -230,6 +230,43 @@ def check_conv_halo(NB=2, H=40, W=64, Cin=128, Cout=128, shortcut=0, residual=Fa
     return worst, tol
 
 
+def check_conv_halo_taps(seed=91):
+    """Halo path with other tap sets: the flipped-tap data gradient of a 3x3 conv and the 2x2 phases of the 4-phase
+    upsample conv (out_mul = 2), each against the per-tap-box path."""
+    L = ops._lib.load()
+    NB, H, W, Cin, Cout = 2, 24, 48, 128, 128
+    x = _rand(NB, H, W, Cin, seed=seed)
+    w = _rand(Cout, Cin, 3, 3, seed=seed + 1, scale=1.0 / math.sqrt(9 * Cin))
+    from diffusion_e2e_ft_b200.backward_packing import pack_conv_dgrad_s1
+    wp, taps = pack_conv_dgrad_s1(w)
+    worst = 0.0
+    outs = []
+    for halo in (2, 0):
+        L.b200_debug_set_halo(halo)
+        try:
+            outs.append(ops.conv2d(x, wp, Cin, taps=taps, out_dtype=torch.float32))
+            torch.cuda.synchronize()
+            assert L.b200_debug_last_path() == (1 if halo else 0)
+        finally:
+            L.b200_debug_set_halo(1)
+    worst = max(worst, rel_l2(outs[0], outs[1]))
+    from diffusion_e2e_ft_b200.modules import Upsample2D
+    m = Upsample2D(Cin).to(DEV)
+    xs = _rand(NB, H, W, Cin, seed=seed + 2, dtype=torch.float32)
+    ys = []
+    with torch.no_grad():
+        for halo in (2, 0):
+            L.b200_debug_set_halo(halo)
+            try:
+                ys.append(m.run(xs, None, torch.float32))
+                torch.cuda.synchronize()
+                assert L.b200_debug_last_path() == (1 if halo else 0)
+            finally:
+                L.b200_debug_set_halo(1)
+    worst = max(worst, rel_l2(ys[0], ys[1]))
+    return worst, 3e-5
+
+
 def check_upsample_conv_phases(NB=2, H=12, W=10, C=128, seed=21):
     """Upsample2D: nearest x2 + conv3x3 computed as four 2x2 convs on the low-res input."""
     from diffusion_e2e_ft_b200.modules import Upsample2D
@@ -641,6 +678,7 @@ CHECKS = {
     "conv_swap_1280_12": lambda: check_conv(NB=2, H=12, W=12, Cin=256, Cout=1280),
     "swap_epilogue_twins_stats": check_swap_epilogue_twins,
     "conv_halo_128": lambda: check_conv_halo(),
+    "conv_halo_dgrad_and_upsample_taps": check_conv_halo_taps,
     "conv_halo_res_f32_stats": lambda: check_conv_halo(H=48, W=96, Cin=64, Cout=256, residual=True, out_f32=True, rowvec=True, stats=True),
     "conv_halo_shortcut_320": lambda: check_conv_halo(NB=1, H=48, W=48, Cin=192, Cout=320, shortcut=128, out_f32=True),
     "conv_halo_edges_768": lambda: check_conv_halo(NB=1, H=35, W=768, Cin=64, Cout=128, seed=73),
