@@ -158,6 +158,15 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erf_v);
 }
 
+// Activation of four values, out of line: the vectorised epilogue's chunk loop is unrolled eight times, and inlining the
+// SiLU / erf-GELU bodies there made it ~1700 SASS instructions of which ~320 execute for a plain conv (ncu r2: 19 % of
+// the epilogue's samples were instruction-fetch stalls).  float4 in / out keeps the values in registers.
+__device__ __noinline__ float4 act4(float4 v, int act) {
+  if (act == ACT_SILU) return make_float4(silu_f(v.x), silu_f(v.y), silu_f(v.z), silu_f(v.w));
+  if (act == ACT_GELU) return make_float4(gelu_erf_f(v.x), gelu_erf_f(v.y), gelu_erf_f(v.z), gelu_erf_f(v.w));
+  return v;
+}
+
 // SWAP = false: accumulator rows (TMEM lanes) = 128 pixels, columns = BLOCK_N output channels.
 // SWAP = true : operands swapped — rows = 128 output channels (weights are the M operand), columns =
 //               BLOCK_N pixels (activations are the N operand).  Used when Cout % 128 == 0: a 128-channel
@@ -468,6 +477,27 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int k = 0; k < 4; ++k) s1[k] = s2[k] = sh[k] = 0.f;
         scnt = 0;
       };
+      // Vectorised path: the offsets of a tile's pixels RELATIVE to its first pixel are the same for every tile, so the
+      // table is built once per CTA (ncu r2: rebuilding it per tile — integer divisions, a 256-thread barrier — was 19 %
+      // of the epilogue's time); per tile only a 64-bit base and the (rows, columns) still inside the image change.
+      uint32_t* s_rel_out = tab;                                   // [BLOCK_N]
+      uint32_t* s_rel_res = tab + BLOCK_N;                         // [BLOCK_N]
+      uint32_t* s_dhdw = tab + 2 * BLOCK_N;                        // [BLOCK_N]  (dh << 16 | dw), dh = 0xFFFF: dead column
+      if (p.vec_ok) {
+        for (int pi = et; pi < BLOCK_N; pi += 32 * kEpiWarps) {
+          int dh = 0, dw = pi;
+          if (p.conv) {
+            dh = pi / p.col_pitch;
+            dw = pi - dh * p.col_pitch;
+            if (dw >= p.bw || dh >= p.bh) dh = 0xFFFF;
+          }
+          const long long rel = p.conv ? ((long long)dh * p.out_mul * p.OW + (long long)dw * p.out_mul) : (long long)pi;
+          s_rel_out[pi] = dh == 0xFFFF ? 0u : (uint32_t)(rel * p.ldo);
+          s_rel_res[pi] = dh == 0xFFFF ? 0u : (uint32_t)(rel * p.ld_res);
+          s_dhdw[pi] = ((uint32_t)dh << 16) | (uint32_t)(dw & 0xFFFF);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_blk = tile % p.n_tiles;                        // channel tile
         int rest = tile / p.n_tiles;
@@ -483,6 +513,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t* t_out = tab + acc * (2 * BLOCK_N);
         uint32_t* t_res = t_out + BLOCK_N;
         uint32_t* t_flag = tab + 4 * BLOCK_N + acc * 8;              // per 32-pixel chunk: all rows valid
+        if (!p.vec_ok) {
         for (int pi = et; pi < BLOCK_N; pi += 32 * kEpiWarps) {
           bool ok;
           long long orow;
@@ -503,6 +534,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if ((et & 31) == 0) t_flag[pi >> 5] = (okmask == 0xffffffffu);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");             // table visible to the 8 epilogue warps
+        }
         const int ch = n_blk * kBlockM + row_in_tile;
         const bool ch_ok = ch < p.N;
         float add = 0.f;
@@ -536,9 +568,22 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (p.rowvec) add4[k] += p.rowvec[(long long)img * p.ld_rowvec + chq + k];
             }
           }
-          OutT* __restrict__ out_q = out + (long long)b * p.out_batch_stride + chq;
-          const OutT* __restrict__ res_q = res ? res + (long long)b * p.res_batch_stride + chq : nullptr;
-          __half* __restrict__ out2_q = p.out2 ? p.out2 + (long long)b * p.out_batch_stride + chq : nullptr;
+          // first pixel of the tile (64-bit) and how many rows / columns of it are inside the image
+          long long pix0;
+          int lim_h, lim_w;
+          if (p.conv) {
+            const int h0 = th * p.bh, w0 = tw * p.bw;
+            pix0 = ((long long)img * p.OH + (h0 * p.out_mul + p.out_oy)) * p.OW + (w0 * p.out_mul + p.out_ox);
+            lim_h = min(p.bh, p.Ho - h0);
+            lim_w = min(p.bw, p.Wo - w0);
+          } else {
+            pix0 = (long long)m_blk * BLOCK_N;
+            lim_h = 1;
+            lim_w = (int)min((long long)BLOCK_N, (long long)p.M - pix0);
+          }
+          OutT* __restrict__ out_q = out + (long long)b * p.out_batch_stride + pix0 * p.ldo + chq;
+          const OutT* __restrict__ res_q = res ? res + (long long)b * p.res_batch_stride + pix0 * p.ld_res + chq : nullptr;
+          __half* __restrict__ out2_q = p.out2 ? p.out2 + (long long)b * p.out_batch_stride + pix0 * p.ldo + chq : nullptr;
           using Vec = typename std::conditional<std::is_same<OutT, float>::value, float4, uint2>::type;
           if (p.chan_stats) {
             // warp-uniform: every lane of the warp switches key on the same tile (invalid channel quads keep key -1)
@@ -559,11 +604,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t oo[8];
               Vec rres[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) oo[i] = cq_ok ? t_out[c + 4 * i + pr] : 0xFFFFFFFFu;
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t dd = s_dhdw[c + 4 * i + pr];
+                const bool ok = cq_ok && (int)(dd >> 16) < lim_h && (int)(dd & 0xFFFFu) < lim_w;
+                oo[i] = ok ? s_rel_out[c + 4 * i + pr] : 0xFFFFFFFFu;
+              }
               if (res_q != nullptr) {                // residual rows first: their latency hides behind the TMEM read
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                  if (oo[i] != 0xFFFFFFFFu) rres[i] = *reinterpret_cast<const Vec*>(res_q + t_res[c + 4 * i + pr]);
+                  if (oo[i] != 0xFFFFFFFFu) rres[i] = *reinterpret_cast<const Vec*>(res_q + s_rel_res[c + 4 * i + pr]);
               }
               uint32_t r[32];
               tmem_ld_32x32(t_row + c, r);
@@ -590,12 +639,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                   for (int k = 0; k < 4; ++k) v[k] += rv4[k];
                 }
-                if (p.act == ACT_SILU) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) v[k] = silu_f(v[k]);
-                } else if (p.act == ACT_GELU) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) v[k] = gelu_erf_f(v[k]);
+                if (p.act != ACT_NONE) {
+                  const float4 a4 = act4(make_float4(v[0], v[1], v[2], v[3]), p.act);
+                  v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w;
                 }
                 if (res_q != nullptr && p.res_mul) {
 #pragma unroll
