@@ -158,23 +158,16 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erf_v);
 }
 
-// Activation of four values, out of line: the vectorised epilogue's chunk loop is unrolled eight times, and inlining the
-// SiLU / erf-GELU bodies there made it ~1700 SASS instructions of which ~320 execute for a plain conv (ncu r2: 19 % of
-// the epilogue's samples were instruction-fetch stalls).  float4 in / out keeps the values in registers.
-__device__ __noinline__ float4 act4(float4 v, int act) {
-  if (act == ACT_SILU) return make_float4(silu_f(v.x), silu_f(v.y), silu_f(v.z), silu_f(v.w));
-  if (act == ACT_GELU) return make_float4(gelu_erf_f(v.x), gelu_erf_f(v.y), gelu_erf_f(v.z), gelu_erf_f(v.w));
-  return v;
-}
-
 // SWAP = false: accumulator rows (TMEM lanes) = 128 pixels, columns = BLOCK_N output channels.
 // SWAP = true : operands swapped — rows = 128 output channels (weights are the M operand), columns =
 //               BLOCK_N pixels (activations are the N operand).  Used when Cout % 128 == 0: a 128-channel
 //               layer then issues 128x256 MMAs (half the operand smem traffic and half the per-k-block
 //               barrier round trips of 128x128), and since lanes = channels the NHWC stores of one
 //               accumulator column are contiguous — no smem transpose in the epilogue.
+// 320 threads, one CTA per SM: 65536 / 320 = 204 registers per thread are available; ptxas's own choice under
+// __launch_bounds__(320, 1) was 168 with spills in the vectorised epilogue, so the cap is stated directly.
 template <int BLOCK_N, typename OutT, bool SWAP, bool GEGLU, bool HALO = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __maxnreg__(200)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   static_assert(!HALO || (SWAP && !GEGLU && BLOCK_N == 256), "halo mode: swapped orientation, 256 accumulator columns");
@@ -620,58 +613,78 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) stgw[j * kSwapPitch + lane] = __uint_as_float(r[j]);
               __syncwarp();
+              // phase A: accumulator * alpha + bias (+ residual) for the lane's 8 pixels x 4 channels
+              float v[8][4];
+              auto res4 = [&](int i, float* r4) {          // the residual / multiplicative operand of pixel i as fp32
+                if constexpr (std::is_same<OutT, float>::value) {
+                  r4[0] = rres[i].x; r4[1] = rres[i].y; r4[2] = rres[i].z; r4[3] = rres[i].w;
+                } else {
+                  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&rres[i].x));
+                  const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&rres[i].y));
+                  r4[0] = f0.x; r4[1] = f0.y; r4[2] = f1.x; r4[3] = f1.y;
+                }
+              };
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 t4 = *reinterpret_cast<const float4*>(stgw + (4 * i + pr) * kSwapPitch + 4 * q);
-                float v[4] = {fmaf(t4.x, p.alpha, add4[0]), fmaf(t4.y, p.alpha, add4[1]), fmaf(t4.z, p.alpha, add4[2]),
-                              fmaf(t4.w, p.alpha, add4[3])};
-                float rv4[4] = {0.f, 0.f, 0.f, 0.f};
-                if (res_q != nullptr && oo[i] != 0xFFFFFFFFu) {
-                  if constexpr (std::is_same<OutT, float>::value) {
-                    rv4[0] = rres[i].x; rv4[1] = rres[i].y; rv4[2] = rres[i].z; rv4[3] = rres[i].w;
-                  } else {
-                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&rres[i].x));
-                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&rres[i].y));
-                    rv4[0] = f0.x; rv4[1] = f0.y; rv4[2] = f1.x; rv4[3] = f1.y;
-                  }
-                }
-                if (res_q != nullptr && !p.res_mul) {
+                v[i][0] = fmaf(t4.x, p.alpha, add4[0]); v[i][1] = fmaf(t4.y, p.alpha, add4[1]);
+                v[i][2] = fmaf(t4.z, p.alpha, add4[2]); v[i][3] = fmaf(t4.w, p.alpha, add4[3]);
+                if (res_q != nullptr && !p.res_mul && oo[i] != 0xFFFFFFFFu) {
+                  float r4[4];
+                  res4(i, r4);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) v[k] += rv4[k];
+                  for (int k = 0; k < 4; ++k) v[i][k] += r4[k];
                 }
-                if (p.act != ACT_NONE) {
-                  const float4 a4 = act4(make_float4(v[0], v[1], v[2], v[3]), p.act);
-                  v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w;
-                }
-                if (res_q != nullptr && p.res_mul) {
+              }
+              // phase B: activations, one contiguous block that a plain conv skips with a single branch (with the SiLU /
+              // GELU bodies interleaved into the unrolled pixel loop, 19 % of the epilogue's samples were instruction-
+              // fetch stalls: ncu r2)
+              if (p.act == ACT_SILU) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) v[k] *= rv4[k];
-                }
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) v[i][k] = silu_f(v[i][k]);
+              } else if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) v[i][k] = gelu_erf_f(v[i][k]);
+              }
+              // phase C: multiplicative operand, stores, statistics
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
                 const bool ok = oo[i] != 0xFFFFFFFFu;
-                __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+                if (res_q != nullptr && p.res_mul && ok) {
+                  float r4[4];
+                  res4(i, r4);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) v[i][k] *= r4[k];
+                }
+                __half2 h01 = __floats2half2_rn(v[i][0], v[i][1]), h23 = __floats2half2_rn(v[i][2], v[i][3]);
                 uint2 hv;
                 hv.x = *reinterpret_cast<uint32_t*>(&h01);
                 hv.y = *reinterpret_cast<uint32_t*>(&h23);
                 if (ok && !(p.debug & 1)) {
                   if constexpr (std::is_same<OutT, float>::value) {
-                    *reinterpret_cast<float4*>(out_q + oo[i]) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(out_q + oo[i]) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
                     if (out2_q != nullptr) *reinterpret_cast<uint2*>(out2_q + oo[i]) = hv;
                   } else {
                     *reinterpret_cast<uint2*>(out_q + oo[i]) = hv;
                   }
                 }
                 if (p.chan_stats && ok) {
+                  float w4[4] = {v[i][0], v[i][1], v[i][2], v[i][3]};
                   if constexpr (!std::is_same<OutT, float>::value) {      // statistics of the values as stored
                     const float2 f0 = __half22float2(h01), f1 = __half22float2(h23);
-                    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+                    w4[0] = f0.x; w4[1] = f0.y; w4[2] = f1.x; w4[3] = f1.y;
                   }
                   if (scnt == 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) sh[k] = v[k];
+                    for (int k = 0; k < 4; ++k) sh[k] = w4[k];
                   }
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const float d = v[k] - sh[k];
+                    const float d = w4[k] - sh[k];
                     s1[k] += d;
                     s2[k] = fmaf(d, d, s2[k]);
                   }
