@@ -164,10 +164,11 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 //               layer then issues 128x256 MMAs (half the operand smem traffic and half the per-k-block
 //               barrier round trips of 128x128), and since lanes = channels the NHWC stores of one
 //               accumulator column are contiguous — no smem transpose in the epilogue.
-// 320 threads, one CTA per SM: 65536 / 320 = 204 registers per thread are available; ptxas's own choice under
-// __launch_bounds__(320, 1) was 168 with spills in the vectorised epilogue, so the cap is stated directly (192: registers are allocated per warp in units of 512, 10 x 6144 <= 65536).
+// 320 threads = 10 warps, one CTA per SM: the busiest scheduler partition hosts three warps and owns 16384 registers,
+// i.e. 170 per thread — the 168 ptxas picks under these launch bounds is the hardware ceiling (a __maxnreg__(192) build
+// fails to launch), not a heuristic.
 template <int BLOCK_N, typename OutT, bool SWAP, bool GEGLU, bool HALO = false>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   static_assert(!HALO || (SWAP && !GEGLU && BLOCK_N == 256), "halo mode: swapped orientation, 256 accumulator columns");
