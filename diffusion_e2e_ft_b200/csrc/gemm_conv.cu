@@ -81,12 +81,12 @@ int sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------
-template <int BN, typename OutT, bool SWAP, bool GEGLU = false, bool HALO = false>
+template <int BN, typename OutT, bool SWAP, bool GEGLU = false, bool HALO = false, bool VEC = false>
 static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
                       const GemmParams& p, cudaStream_t st) {
   using S = GemmSmem<BN, SWAP, HALO>;
   static bool configured = false;
-  auto kern = gemm_conv_kernel<BN, OutT, SWAP, GEGLU, HALO>;
+  auto kern = gemm_conv_kernel<BN, OutT, SWAP, GEGLU, HALO, VEC>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes);
     if (e != cudaSuccess) {
@@ -110,9 +110,12 @@ static int launch_bn(int bn, bool swap, const CUtensorMap& a, const CUtensorMap&
                      const GemmParams& p, cudaStream_t st) {
   if (swap) {
     switch (bn) {
-      case 64: return launch_one<64, OutT, true>(a, a2, b, p, st);
-      case 128: return launch_one<128, OutT, true>(a, a2, b, p, st);
-      case 256: return launch_one<256, OutT, true>(a, a2, b, p, st);
+      case 64: return p.vec_ok ? launch_one<64, OutT, true, false, false, true>(a, a2, b, p, st)
+                               : launch_one<64, OutT, true>(a, a2, b, p, st);
+      case 128: return p.vec_ok ? launch_one<128, OutT, true, false, false, true>(a, a2, b, p, st)
+                                : launch_one<128, OutT, true>(a, a2, b, p, st);
+      case 256: return p.vec_ok ? launch_one<256, OutT, true, false, false, true>(a, a2, b, p, st)
+                                : launch_one<256, OutT, true>(a, a2, b, p, st);
     }
   } else if (p.act == ACT_GEGLU) {
     if constexpr (std::is_same<OutT, __half>::value) {
@@ -365,7 +368,9 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
     // output element against ~1 us of MMA per tile) gain nothing from cheaper operand loads and lose ~10 % to the dead
     // halo columns their epilogue still walks: r2 bench, 128->128 768^2 fp32: 740 (halo) vs 825 TFLOP/s (per-tap boxes)
     const bool epi_bound = out_f32 && residual && num_taps * Cin <= 1152 && !X2;
-    if (can_swap && g_halo_mode && taps_ok && !g_force_bn && (!epi_bound || g_halo_mode == 2) &&
+    const bool halo_vec = !(g_debug & 64) && (Cout % 4 == 0) && (!residual || ((uintptr_t)residual & 15) == 0) &&
+                          (!out2_f16 || ((uintptr_t)out2_f16 & 7) == 0);      // the halo kernel has the vectorised epilogue only
+    if (can_swap && g_halo_mode && taps_ok && !g_force_bn && halo_vec && (!epi_bound || g_halo_mode == 2) &&
         pick_halo_tile(Ho, Wo, &hbw, &hbh)) {
       p.bw = hbw; p.bh = hbh;
       p.col_pitch = hbw + 2;
@@ -387,8 +392,7 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
       p.residual = residual; p.ld_res = Cout;
       p.act = act; p.alpha = 1.0f; p.debug = g_debug;
       p.chan_stats = chan_stats; p.out2 = (__half*)out2_f16;
-      p.vec_ok = !(g_debug & 64) && (Cout % 4 == 0) && (!residual || ((uintptr_t)residual & 15) == 0) &&
-                 (!out2_f16 || ((uintptr_t)out2_f16 & 7) == 0);
+      p.vec_ok = 1;
       CUtensorMap ta, ta2, tb;
       {
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
@@ -415,8 +419,8 @@ extern "C" int b200_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, co
       }
       cudaStream_t st = (cudaStream_t)stream;
       g_last_path = 1;
-      return out_f32 ? launch_one<256, float, true, false, true>(ta, ta2, tb, p, st)
-                     : launch_one<256, __half, true, false, true>(ta, ta2, tb, p, st);
+      return out_f32 ? launch_one<256, float, true, false, true, true>(ta, ta2, tb, p, st)
+                     : launch_one<256, __half, true, false, true, true>(ta, ta2, tb, p, st);
     }
   }
   g_last_path = 0;

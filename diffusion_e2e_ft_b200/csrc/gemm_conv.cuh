@@ -167,11 +167,16 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 // 320 threads = 10 warps, one CTA per SM: the busiest scheduler partition hosts three warps and owns 16384 registers,
 // i.e. 170 per thread — the 168 ptxas picks under these launch bounds is the hardware ceiling (a __maxnreg__(192) build
 // fails to launch), not a heuristic.
-template <int BLOCK_N, typename OutT, bool SWAP, bool GEGLU, bool HALO = false>
+// VEC (swapped orientation only): the vectorised epilogue (smem transpose, 16-byte accesses, statistics carried across
+// tiles) INSTEAD of the direct lane = channel one; a template parameter so that each instantiation carries one epilogue
+// only — with both compiled in, the small-K GEMMs of the transformer blocks (epilogue-bound) lost 25 % to spills and
+// instruction-cache misses (r2 bench: 14.1 -> 16.2 ms of linear GEMMs per step).
+template <int BLOCK_N, typename OutT, bool SWAP, bool GEGLU, bool HALO = false, bool VEC = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  static_assert(!HALO || (SWAP && !GEGLU && BLOCK_N == 256), "halo mode: swapped orientation, 256 accumulator columns");
+  static_assert(!HALO || (SWAP && !GEGLU && BLOCK_N == 256 && VEC), "halo mode: swapped orientation, 256 accumulator columns");
+  static_assert(!VEC || SWAP, "the vectorised epilogue belongs to the swapped orientation");
   using S = GemmSmem<BLOCK_N, SWAP, HALO>;
   constexpr int kStages = S::kStages;
   // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array itself, so
@@ -477,7 +482,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t* s_rel_out = tab;                                   // [BLOCK_N]
       uint32_t* s_rel_res = tab + BLOCK_N;                         // [BLOCK_N]
       uint32_t* s_dhdw = tab + 2 * BLOCK_N;                        // [BLOCK_N]  (dh << 16 | dw), dh = 0xFFFF: dead column
-      if (p.vec_ok) {
+      if constexpr (VEC) {
         for (int pi = et; pi < BLOCK_N; pi += 32 * kEpiWarps) {
           int dh = 0, dw = pi;
           if (p.conv) {
@@ -507,7 +512,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t* t_out = tab + acc * (2 * BLOCK_N);
         uint32_t* t_res = t_out + BLOCK_N;
         uint32_t* t_flag = tab + 4 * BLOCK_N + acc * 8;              // per 32-pixel chunk: all rows valid
-        if (!p.vec_ok) {
+        if constexpr (!VEC) {
         for (int pi = et; pi < BLOCK_N; pi += 32 * kEpiWarps) {
           bool ok;
           long long orow;
@@ -543,7 +548,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float st1 = 0.f, st2 = 0.f, st_shift = 0.f;     // sums of (v - shift), (v - shift)^2 over this thread's pixels
         int st_cnt = 0;
 
-        if (p.vec_ok) {
+        if constexpr (VEC) {
           // ---------------------------------------------------------------- vectorised path (16-byte accesses)
           // TMEM hands each lane ONE channel of 32 pixels; NHWC wants, per pixel, runs of consecutive channels.  Each
           // 32x32 chunk goes through a per-warp smem tile (STS.32 by pixel row, LDS.128 back): afterwards lane
@@ -791,7 +796,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
-      if (p.chan_stats && p.vec_ok && __any_sync(0xffffffffu, scnt > 0)) flush_stats();
+      if (VEC && p.chan_stats && __any_sync(0xffffffffu, scnt > 0)) flush_stats();
     } else {
     float (*stg)[33] = reinterpret_cast<float (*)[33]>(stage_smem + ew * (32 * 33 * 4));
     // per-warp row tables (16-byte aligned): element offsets of each of the warp's 32 rows relative to the
