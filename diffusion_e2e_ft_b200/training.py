@@ -110,11 +110,13 @@ class FlatTrainer:
     that runs first in forward) get their own bucket, so they do not hold the others back.  With `overlap=True` a
     bucket's SUM all-reduce is launched asynchronously (NCCL stream) the moment autograd has accumulated its last
     parameter, as accelerate's DDP does for the reference; the DEFAULT is `overlap=False` — all buckets are reduced in
-    `step()` after backward — because on this engine overlap is a loss: the GEMM / conv kernels are persistent with one
-    200 KB-smem CTA per SM, so while NCCL's channel CTAs occupy SMs a 148-CTA grid no longer fits in one wave and the
-    backward kernels take two (measured on 2 x B200, bs 2 768^2: 515 ms / step with overlap vs 260 ms without, against
-    5.7 ms for the 3.46 GB all-reduce alone at 604 GB/s bus bandwidth: profiles/bench_r02_n2.json).  The 1/world_size
-    of the average is folded into the optimizer kernel's gradient multiplier (no extra pass over the 3.46 GB buffer).
+    `step()` after backward — because on this engine overlap can be a large loss: the GEMM / conv kernels are persistent
+    with one 200 KB-smem CTA per SM, so while NCCL's channel CTAs occupy SMs a 148-CTA grid no longer fits in one wave
+    and the backward kernels take two.  Measured, bs 2 768^2 per rank: 2 x B200 (P2P ring) 515 ms / step with overlap vs
+    260 ms without, against 5.7 ms for the 3.46 GB all-reduce alone (604 GB/s bus bandwidth); 8 x B200 (NVLS, few
+    CTAs) 178 vs 182 ms with 7.3 ms alone (827 GB/s) — profiles/bench_r02_n2.json, bench_r02_n8.json.  Exposing 4 % of
+    the step is the safe choice at every N.  The 1/world_size of the average is folded into the optimizer kernel's
+    gradient multiplier (no extra pass over the 3.46 GB buffer).
 
     Mixed precision: backward GEMM operands are fp16, so the loss is multiplied by a loss scale held ON THE DEVICE
     (`state[0]`); the fused optimizer kernel skips the step and halves the scale when the gradient norm is non-finite,

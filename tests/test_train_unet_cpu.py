@@ -68,7 +68,7 @@ dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29587", rank=r, wor
 unet_ref, vae_ref = MG.build_tiny()
 unet, vae = E.engine_from_oracle(unet_ref, vae_ref, "cpu")
 unet.requires_grad_(True)
-tr = FlatTrainer(unet, lr=1e-4, bucket_mb=0.25, accumulation_steps=2)   # many buckets: async all-reduce per bucket
+tr = FlatTrainer(unet, lr=1e-4, bucket_mb=0.25, accumulation_steps=2, overlap=True)   # many buckets: async all-reduce per bucket, launched from the backward hooks
 assert len(tr._buckets) > 4
 late = sum((p.numel() + 3) // 4 * 4 for n, p in unet.named_parameters() if any(k in n for k in tr.LATE_GRAD_KEYS))
 assert any(b["hi"] == late for b in tr._buckets)        # late-gradient parameters lead the flat order, own bucket(s)
