@@ -366,8 +366,10 @@ extern "C" int b200_attention_d64(const void* q, long long q_bs, long long q_ls,
     r = encode_tmap(&tv, v, 3, dims, strv, box, nullptr);
     if (r) return r;
   }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured_dev[kMaxDevices] = {false};      // per device: function attributes live in the context
+  const int dev_ = current_device();
+  bool& configured = configured_dev[dev_ < 0 ? 0 : dev_];
+  if (!configured || dev_ < 0) {
     cudaError_t e = cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(attention smem=%d): %s", kAttSmem, cudaGetErrorString(e));

@@ -216,6 +216,8 @@ int encode_tmap(CUtensorMap* out, const void* gptr, int rank, const uint64_t* di
                 const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
                 const uint32_t* elem_strides, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
 
-int sm_count();
+int sm_count();            // of the CURRENT device (cached per device)
+int current_device();      // cudaGetDevice, -1 on error
+constexpr int kMaxDevices = 64;   // per-device caches (function attributes are per context: one flag per device and kernel)
 
 }  // namespace b200

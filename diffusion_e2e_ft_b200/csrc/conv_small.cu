@@ -106,8 +106,10 @@ extern "C" int b200_conv3x3_small_cout(const void* x, int NB, int H, int W, int 
   B200_CHECK_ARG(x && wq && out && NB > 0 && H > 0 && W > 0, "b200_conv3x3_small_cout: bad arguments");
   B200_CHECK_ARG(C % kCC == 0 && Cout >= 1 && Cout <= 8, "b200_conv3x3_small_cout: C=%d must be a multiple of 64, Cout=%d <= 8", C, Cout);
   B200_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wq & 15) == 0, "b200_conv3x3_small_cout: 16-byte alignment");
-  static bool configured = false;
-  if (!configured) {
+  static bool configured_dev[kMaxDevices] = {false};      // per device: function attributes live in the context
+  const int dev_ = current_device();
+  bool& configured = configured_dev[dev_ < 0 ? 0 : dev_];
+  if (!configured || dev_ < 0) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_small_cout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmem);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(conv_small smem=%d): %s", kSmallSmem, cudaGetErrorString(e));

@@ -69,15 +69,21 @@ int encode_tmap(CUtensorMap* out, const void* gptr, int rank, const uint64_t* di
   return 0;
 }
 
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices ? dev : -1;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};          // immutable once written; a racing first call writes the same value
+  const int dev = current_device();
+  if (dev < 0) return 148;
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -85,9 +91,11 @@ template <int BN, typename OutT, bool SWAP, bool GEGLU = false, bool HALO = fals
 static int launch_one(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b,
                       const GemmParams& p, cudaStream_t st) {
   using S = GemmSmem<BN, SWAP, HALO>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {false};      // the attribute belongs to the (device) context
+  const int dev = current_device();
+  bool& configured = configured_dev[dev < 0 ? 0 : dev];
   auto kern = gemm_conv_kernel<BN, OutT, SWAP, GEGLU, HALO, VEC>;
-  if (!configured) {
+  if (!configured || dev < 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes);
     if (e != cudaSuccess) {
       set_last_error("cudaFuncSetAttribute(smem=%d): %s", S::kTotalBytes, cudaGetErrorString(e));
