@@ -192,15 +192,22 @@ def conv_dgrad(dy, w, cin, kind="s1", out_dtype=F32, add=None, packed=None, in_h
 
 # --------------------------------------------------------------------------------------------- attention
 def attention_bwd(q, k, v, do, heads, scale, outs=None):
-    """Backward of softmax(scale * q k^T) v per head (head dim 64), by recomputation: S and dP on the GEMM kernel,
-    row softmax + its backward, then dQ = dS K, dK = dS^T Q, dV = P^T dO.  q/do [B,T,heads*64], k/v [B,Tk,heads*64]
-    fp16 views (last dim contiguous).  Returns fp16 (dq, dk, dv) — written into `outs` (row-strided views, e.g. the
-    three column blocks of a fused d(qkv) buffer) when given.  Materialises [heads, T, Tk] per image — the fused
-    flash backward replaces this once the rest of a10 is in place."""
+    """Backward of softmax(scale * q k^T) v per head (head dim 64).  q/do [B,T,heads*64], k/v [B,Tk,heads*64] fp16
+    views (last dim contiguous).  Returns fp16 (dq, dk, dv) — written into `outs` (row-strided views, e.g. the three
+    column blocks of a fused d(qkv) buffer) when given.
+
+    Round 2: no fp32 score matrices and no softmax passes.  The flash kernel is re-run for (O, log-sum-exp); then per
+    image, batched over heads,
+        P  = exp2(c * Q K^T - lse)                     GEMM with an exp2 epilogue (row bias -lse), fp16 out
+        dS = scale * P o (dO V^T - delta)              GEMM with a row bias (-scale * delta) and P as multiplicative operand
+        dQ = dS K,  dK = dS^T Q,  dV = P^T dO          row contractions, operands consumed MN-major as stored
+    with delta_t = sum_d dO_td O_td (`rowdot_heads`).  Round 1 materialised S and dP in fp32, ran a row softmax and its
+    backward over them and transposed dS / P / Q / K / dO with a gather kernel: ~125 of 254 ms of a bs-2 768^2 iteration.
+    Still materialises P and dS ([heads, T, Tk] fp16 per image): a fused flash backward would remove those too."""
     B, T, C = q.shape
     Tk = k.shape[1]
     assert C == heads * 64
-    Tkp, T8 = ops._ru8(Tk), ops._ru8(T)
+    Tkp = ops._ru8(Tk)
     dev = q.device
     if outs is not None:
         dq, dk, dv = outs
@@ -213,20 +220,26 @@ def attention_bwd(q, k, v, do, heads, scale, outs=None):
     def heads_view(t2d):                      # [L, heads*64] -> [heads, L, 64] strided view
         return t2d.unflatten(-1, (heads, 64)).permute(1, 0, 2)
 
+    o, lse = ops.attention_d64(q, k, v, heads, scale, want_lse=True)          # [B,T,C], [B,heads,T] (log2 domain)
+    delta = ops.rowdot_heads(do, o, heads)                                   # [B,heads,T]
+    neg_lse = _scaled(lse, -1.0)
+    neg_delta = _scaled(delta, -float(scale))
+    c = float(scale) * 1.4426950408889634
     for b in range(B):
         qh, kh, vh, doh = heads_view(q[b]), heads_view(k[b]), heads_view(v[b]), heads_view(do[b])
-        s = torch.zeros((heads, T, Tkp), dtype=F32, device=dev)
-        ops.linear(qh, kh, out=s[:, :, :Tk], out_dtype=F32)
-        p = ops.softmax_rows(s, scale, cols=Tk)                          # [heads, T, Tkp] fp16, padding 0
-        dp = torch.zeros((heads, T, Tkp), dtype=F32, device=dev)
-        ops.linear(doh, vh, out=dp[:, :, :Tk], out_dtype=F32)
-        ds = ops.softmax_bwd_rows(p, dp, scale, cols=Tk)                 # [heads, T, Tkp] fp16, padding 0
-        del s, dp
-        # The three products contract over rows of row-major tensors; the GEMM kernel consumes them MN-major as stored
-        # (round 1 transposed dS, P, Q, K, dO through `gather_planar`: 84 of 254 ms of a bs-2 768^2 iteration).
+        p = torch.empty((heads, T, Tkp), dtype=F16, device=dev)
+        ops.linear(qh, kh, bias=neg_lse[b], bias_row=True, act=ops.ACT_EXP2, alpha=c, out=p[:, :, :Tk])
+        ds = torch.empty((heads, T, Tkp), dtype=F16, device=dev)
+        ops.linear(doh, vh, bias=neg_delta[b], bias_row=True, alpha=float(scale), residual=p[:, :, :Tk], res_mul=True,
+                   out=ds[:, :, :Tk])
         # dQ[h] = dS[h] @ K[h]            (K [Tk, 64] = [contraction, columns])
         ops.linear(ds[:, :, :Tk], kh, out=heads_view(dq[b]), w_t=True)
         # dK[h] = dS[h]^T @ Q[h], dV[h] = P[h]^T @ dO[h]   (contraction over the T query rows of both operands)
         ops.linear(ds[:, :, :Tk], qh, out=heads_view(dk[b]), a_t=True, w_t=True)
         ops.linear(p[:, :, :Tk], doh, out=heads_view(dv[b]), a_t=True, w_t=True)
     return dq, dk, dv
+
+
+def _scaled(t, f):
+    """f * t for a small fp32 per-row vector ([B, heads, T] softmax statistics): host-level plumbing, O(rows)."""
+    return (t * f).contiguous()

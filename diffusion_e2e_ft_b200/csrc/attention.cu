@@ -33,6 +33,7 @@ struct AttParams {
   float scale_log2;
   __half* out;
   long long o_bs, o_ls;
+  float* lse;                  // optional [B][heads][Lq]: log2-domain log-sum-exp of the scaled scores (backward pass)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -309,6 +310,8 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
     const int qrow = q0 + w * kBq + row;
+    if (qrow < p.Lq && p.lse != nullptr)          // P_ij = exp2(S_ij * c - lse): what the backward pass recomputes P from
+      p.lse[((long long)b * p.heads + h) * p.Lq + qrow] = fmaf(m, c, log2f(l));
     if (qrow < p.Lq) {
       const float inv = 1.0f / l;
       __half* dst = p.out + (long long)b * p.o_bs + (long long)qrow * p.o_ls + h * kD;
@@ -339,7 +342,7 @@ using namespace b200;
 extern "C" int b200_attention_d64(const void* q, long long q_bs, long long q_ls, const void* k,
                                   long long k_bs, long long k_ls, const void* v, long long v_bs,
                                   long long v_ls, void* out, long long o_bs, long long o_ls, int B,
-                                  int heads, int Lq, int Lk, int kv_segments, float scale,
+                                  int heads, int Lq, int Lk, int kv_segments, float scale, float* lse,
                                   void* stream) {
   B200_CHECK_ARG(q && k && v && out, "b200_attention_d64: null pointer");
   B200_CHECK_ARG(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "b200_attention_d64: bad shape");
@@ -381,6 +384,7 @@ extern "C" int b200_attention_d64(const void* q, long long q_bs, long long q_ls,
   p.B = B; p.heads = heads; p.Lq = Lq; p.Lk = Lk; p.kv_segments = kv_segments;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = (__half*)out; p.o_bs = o_bs; p.o_ls = o_ls;
+  p.lse = lse;
   dim3 grid((Lq + kWG * kBq - 1) / (kWG * kBq), heads, B);
   attention_d64_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tq, tk, tv, p);
   B200_CHECK_LAUNCH("attention_d64_kernel");

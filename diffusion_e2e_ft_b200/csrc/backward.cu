@@ -102,6 +102,25 @@ __global__ void gather_planar_kernel(const T* __restrict__ x, long long ldx, int
   }
 }
 
+// ------------------------------------------------------------------------------------------------ rowdot
+// delta[b][h][t] = sum_{d < 64} a[b][t][h*64 + d] * c[b][t][h*64 + d]   (fp16 in, fp32 accumulate / out).
+// One warp per (t, h): 64 elements = one __half2 per lane.
+__global__ void rowdot_heads_kernel(const __half* __restrict__ a, long long a_bs, long long a_ls,
+                                    const __half* __restrict__ c, long long c_bs, long long c_ls, int L, int heads,
+                                    float* __restrict__ out) {
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= L) return;
+  const int lane = threadIdx.x & 31;
+  const __half2 x = *reinterpret_cast<const __half2*>(a + (long long)b * a_bs + (long long)t * a_ls + h * 64 + 2 * lane);
+  const __half2 y = *reinterpret_cast<const __half2*>(c + (long long)b * c_bs + (long long)t * c_ls + h * 64 + 2 * lane);
+  const float2 xf = __half22float2(x), yf = __half22float2(y);
+  float s = fmaf(xf.x, yf.x, xf.y * yf.y);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[((long long)b * heads + h) * L + t] = s;
+}
+
 // ------------------------------------------------------------------------------------------------ col_sum
 // out[c] += sum over rows of x[row][c];  grid (ceil(C/32), row chunks), block (32, 8).
 template <typename T>
@@ -617,6 +636,18 @@ extern "C" int b200_gather_planar(const void* x, int in_f32, long long ldx, int 
     gather_planar_kernel<__half><<<grid, block, 0, st>>>((const __half*)x, ldx, H, W, C, Ho, Wo, stride, up, oy, ox, P, Ppad,
                                                          (__half*)out, ldo);
   B200_CHECK_LAUNCH("gather_planar_kernel");
+  return 0;
+}
+
+extern "C" int b200_rowdot_heads(const void* a, long long a_bs, long long a_ls, const void* c, long long c_bs,
+                                 long long c_ls, int B, int L, int heads, float* out, void* stream) {
+  B200_CHECK_ARG(a && c && out && B > 0 && L > 0 && heads > 0, "b200_rowdot_heads: bad arguments");
+  B200_CHECK_ARG(a_ls % 2 == 0 && c_ls % 2 == 0 && a_bs % 2 == 0 && c_bs % 2 == 0 &&
+                     (((uintptr_t)a | (uintptr_t)c) & 3) == 0, "b200_rowdot_heads: 4-byte alignment");
+  dim3 grid((L + 7) / 8, heads, B);
+  rowdot_heads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)a, a_bs, a_ls, (const __half*)c, c_bs, c_ls, L,
+                                                              heads, out);
+  B200_CHECK_LAUNCH("rowdot_heads_kernel");
   return 0;
 }
 

@@ -197,7 +197,7 @@ extern "C" void b200_debug_set_flags(int f) { b200::g_debug = f; }
 extern "C" void b200_debug_set_swap(int m) { b200::g_swap_mode = m; }
 extern "C" void b200_debug_set_halo(int m) { b200::g_halo_mode = m; }
 extern "C" int b200_debug_last_path(void) { return b200::g_last_path; }
-extern "C" int b200_abi_version(void) { return 3; }
+extern "C" int b200_abi_version(void) { return 4; }
 // Tile width used by the GEGLU epilogue for a packed width N (= 2 x output width); weights must be
 // packed per tile as [value half | gate half] with this width.
 extern "C" int b200_geglu_block_n(int N) {
@@ -210,7 +210,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
                            long long res_batch_stride, void* out, long long ldo,
                            long long out_batch_stride, int out_f32, int act, float alpha,
                            double* chan_stats, int rows_per_img, void* out2_f16, int res_mul, int a_mn, int w_mn,
-                           void* stream) {
+                           long long bias_batch_stride, void* stream) {
   B200_CHECK_ARG(A && W && out, "b200_linear: null pointer");
   B200_CHECK_ARG(!(a_mn || w_mn) || act != ACT_GEGLU, "b200_linear: MN-major operands are not combined with GEGLU");
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "b200_linear: bad shape M=%d N=%d K=%d batch=%d", M, N, K, batch);
@@ -276,6 +276,7 @@ extern "C" int b200_linear(const void* A, long long lda, long long a_batch_strid
   p.act = act; p.alpha = alpha; p.debug = g_debug;
   p.chan_stats = chan_stats; p.rows_per_img = rows_per_img; p.out2 = (__half*)out2_f16;
   p.act_mn = a_mn; p.w_mn = w_mn;
+  p.bias_bs = bias_batch_stride;
   p.out_mul = 1;
   // swapped epilogue: 16-byte (fp32) / 8-byte (fp16) accesses over runs of 4 channels
   {

@@ -31,7 +31,7 @@ constexpr int kAccStages = 2;
 constexpr int kAccStrideCols = 256;
 constexpr int kMaxTaps = 9;
 
-enum EpiAct { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_GELU = 3 };
+enum EpiAct { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_GELU = 3, ACT_EXP2 = 4 };   // EXP2: P = exp2(alpha S - lse)
 
 struct GemmParams {
   int M, N, num_k_blocks;
@@ -61,6 +61,7 @@ struct GemmParams {
   int out_nchw;                // conv only: write fp32/fp16 NCHW (small Cout) instead of NHWC
   const float* bias;           // [N] (or [M] when bias_row)
   int bias_row;
+  long long bias_bs;           // bias_row: element offset of the bias vector per batch index
   const float* rowvec;         // per-image vector, indexed [img*ld_rowvec + col]
   long long ld_rowvec;
   int res_mul;                 // residual operand multiplies (out = act(acc+bias) * residual) instead of adding
@@ -841,7 +842,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       s_off_out[lane] = row_ok ? (uint32_t)(orow * p.ldo) : 0xFFFFFFFFu;
       s_off_res[lane] = (uint32_t)(orow * p.ld_res);
-      s_bias_r[lane] = (bias && p.bias_row && row_ok) ? bias[orow] : 0.f;
+      s_bias_r[lane] = (bias && p.bias_row && row_ok) ? bias[(long long)b * p.bias_bs + orow] : 0.f;
       __syncwarp();
       OutT* __restrict__ out_b = out + (long long)b * p.out_batch_stride;
       const OutT* __restrict__ res_b = res ? res + (long long)b * p.res_batch_stride : nullptr;
@@ -956,6 +957,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else if (p.act == ACT_GELU) {
 #pragma unroll
               for (int rr = 0; rr < 32; ++rr) vals[rr] = gelu_erf_f(vals[rr]);
+            } else if (p.act == ACT_EXP2) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) vals[rr] = exp2f(vals[rr]);
             }
             if (res_b != nullptr && p.res_mul) {
 #pragma unroll

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200_e2eft.so")
 
 _lib = None
-ABI_VERSION = 3          # bumped with every signature change of include/b200_e2eft.h
+ABI_VERSION = 4          # bumped with every signature change of include/b200_e2eft.h
 
 _P = c_void_p
 _LL = c_longlong
@@ -25,7 +25,7 @@ _SIGS = {
     "b200_debug_last_path": (c_int, []),
     "b200_geglu_block_n": (c_int, [c_int]),
     "b200_linear": (c_int, [_P, _LL, _LL, _P, _LL, _LL, c_int, c_int, c_int, c_int, _P, c_int, _P, _LL, _LL,
-                            _P, _LL, _LL, c_int, c_int, c_float, _P, c_int, _P, c_int, c_int, c_int, _P]),
+                            _P, _LL, _LL, c_int, c_int, c_float, _P, c_int, _P, c_int, c_int, c_int, _LL, _P]),
     "b200_conv2d_nhwc": (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int,
                                  POINTER(c_int), POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int,
                                  _P, _P, _LL, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
@@ -38,7 +38,8 @@ _SIGS = {
                                          c_int, _P, _P, _P]),
     "b200_layer_norm": (c_int, [_P, c_int, _LL, c_int, _P, _P, c_float, _P, _P]),
     "b200_attention_d64": (c_int, [_P, _LL, _LL, _P, _LL, _LL, _P, _LL, _LL, _P, _LL, _LL, c_int, c_int, c_int,
-                                   c_int, c_int, c_float, _P]),
+                                   c_int, c_int, c_float, _P, _P]),
+    "b200_rowdot_heads": (c_int, [_P, _LL, _LL, _P, _LL, _LL, c_int, c_int, c_int, _P, _P]),
     "b200_softmax_rows": (c_int, [_P, _LL, _P, _LL, _LL, c_int, c_float, _P]),
     "b200_softmax_groups": (c_int, [_P, c_int, _LL, c_int, c_int, _P, c_int, _P]),
     "b200_upsample_nearest_nhwc": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),

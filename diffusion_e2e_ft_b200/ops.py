@@ -11,7 +11,7 @@ import torch
 
 from . import lib as _lib
 
-ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_EXP2 = 0, 1, 2, 3, 4
 F16, F32 = torch.float16, torch.float32
 
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]        # pad=1
@@ -173,7 +173,7 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ACT_NONE
         (residual.stride(0) if (residual is not None and batched) else 0),
         _p(out), out.stride(-2), out.stride(0) if batched else 0, int(out.dtype == F32),
         act, float(alpha), _p(cs), int(stats_rows_per_img) if cs is not None else 0, _p(h16), int(res_mul),
-        int(a_t), int(w_t), _stream())
+        int(a_t), int(w_t), (bias.stride(0) if (bias is not None and bias_row and bias.dim() == 2) else 0), _stream())
     _lib.check(rc, "b200_linear")
     STATS.add("linear", 2 * B * M * N * K)
     if ev is not None:
@@ -317,8 +317,10 @@ def layer_norm(x, gamma, beta, eps=1e-5):
 
 # ------------------------------------------------------------------------------ attention
 @_timed("attention")
-def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None):
-    """q: [B,Lq,>=heads*64] view, k/v: [B,Lk,...] views (fp16, last dim contiguous) -> [B,Lq,heads*64]."""
+def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None, want_lse=False):
+    """q: [B,Lq,>=heads*64] view, k/v: [B,Lk,...] views (fp16, last dim contiguous) -> [B,Lq,heads*64].
+    `want_lse`: also return the log2-domain log-sum-exp of the scaled scores, fp32 [B, heads, Lq]
+    (P_ij = exp2(scale * log2(e) * S_ij - lse_i)) for the backward pass."""
     _need_cuda(q, k, v)
     assert q.dtype == F16 and k.dtype == F16 and v.dtype == F16
     assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
@@ -329,11 +331,24 @@ def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None):
     kb = k.stride(0) if k.shape[0] > 1 else k.stride(1) * Lk
     vb = v.stride(0) if v.shape[0] > 1 else v.stride(1) * Lk
     qb = q.stride(0) if B > 1 else q.stride(1) * Lq
+    lse = torch.empty((B, heads, Lq), dtype=F32, device=q.device) if want_lse else None
     rc = _lib.load().b200_attention_d64(_p(q), qb, q.stride(1), _p(k), kb, k.stride(1), _p(v), vb, v.stride(1),
                                         _p(out), out.stride(0) if B > 1 else out.stride(1) * Lq, out.stride(1),
-                                        B, heads, Lq, Lk, kv_segments, float(scale), _stream())
+                                        B, heads, Lq, Lk, kv_segments, float(scale), _p(lse), _stream())
     _lib.check(rc, "b200_attention_d64")
     STATS.add("attn", 4 * B * heads * Lq * Lk * kv_segments * 64)
+    return (out, lse) if want_lse else out
+
+
+@_timed("bwd_misc")
+def rowdot_heads(a, c, heads):
+    """delta[b, h, t] = sum_d a[b, t, h*64+d] * c[b, t, h*64+d]; a, c fp16 [B, L, >=heads*64] views -> fp32 [B, heads, L]."""
+    _need_cuda(a, c)
+    assert a.dtype == F16 and c.dtype == F16 and a.stride(-1) == 1 and c.stride(-1) == 1 and a.shape[:2] == c.shape[:2]
+    B, L = a.shape[0], a.shape[1]
+    out = torch.empty((B, heads, L), dtype=F32, device=a.device)
+    _ck(_lib.load().b200_rowdot_heads(_p(a), a.stride(0), a.stride(1), _p(c), c.stride(0), c.stride(1), B, L, heads,
+                                      _p(out), _stream()), "b200_rowdot_heads")
     return out
 
 

@@ -32,6 +32,7 @@ int b200_abi_version(void);
 #define B200_ACT_SILU 1
 #define B200_ACT_GEGLU 2 /* W rows pre-interleaved per tile: [value half | gate half] */
 #define B200_ACT_GELU 3  /* erf GELU */
+#define B200_ACT_EXP2 4  /* exp2(alpha * acc + bias): softmax probabilities recomputed from the log-sum-exp */
 
 /* out[b][m][n] = act( alpha * sum_k A[b][m][k] * W[(b)][n][k] + bias + residual[b][m][n] )
  * tcgen05 GEMM, fp16 operands (K contiguous), fp32 accumulate in TMEM.
@@ -57,6 +58,7 @@ int b200_linear(const void* A, long long lda, long long a_batch_stride,
                 int a_mn /* 1: A is stored [K][M] (row pitch lda >= M): out = A^T-as-stored x W^T without a transposition
                             pass (MN-major UMMA operand).  Weight gradients dW = dY^T X, attention backward dK = dS^T Q */,
                 int w_mn /* 1: W is stored [K][N] (row pitch ldw >= N): data gradients dX = dY W, dQ = dS K */,
+                long long bias_batch_stride /* bias_row with batch > 1: bias of batch b starts at bias + b * stride */,
                 void* stream);
 
 /* GEGLU tile width for packed width N (weights/bias rows are interleaved per tile of this width:
@@ -131,7 +133,10 @@ int b200_attention_d64(const void* q, long long q_bs, long long q_ls,
                        const void* k, long long k_bs, long long k_ls,
                        const void* v, long long v_bs, long long v_ls,
                        void* out, long long o_bs, long long o_ls,
-                       int B, int heads, int Lq, int Lk, int kv_segments, float scale, void* stream);
+                       int B, int heads, int Lq, int Lk, int kv_segments, float scale,
+                       float* lse /* optional [B][heads][Lq] fp32: log2-domain log-sum-exp of the scaled scores, so that
+                                     P_ij = exp2(scale * log2(e) * S_ij - lse_i) — the backward pass recomputes P from it */,
+                       void* stream);
 
 /* Row softmax: P[r][:] = softmax(scale * S[r][:]) fp32 -> fp16 (VAE mid-block attention, d=512). */
 int b200_softmax_rows(const float* S, long long lds, void* P, long long ldp, long long rows,
@@ -220,6 +225,10 @@ int b200_adamw_step_state(float* param, const float* grad, float* exp_avg, float
 int b200_gather_planar(const void* x, int in_f32, long long ldx, int NB, int H, int W, int C, int Ho, int Wo, int stride, int up,
                        int oy, int ox, void* out, long long ldo, void* stream);
 int b200_col_sum(const void* x, int in_f32, long long rows, int C, long long ld, float* out, void* stream);
+/* delta[b][h][t] = sum_d a[b,t,h*64+d] * c[b,t,h*64+d] (fp16 in, fp32 out): the row term of the softmax backward,
+ * dS = scale * P o (dP - delta), with a = dO and c = O (attention backward, attention.py:497). */
+int b200_rowdot_heads(const void* a, long long a_bs, long long a_ls, const void* c, long long c_bs, long long c_ls,
+                      int B, int L, int heads, float* out, void* stream);
 int b200_group_norm_mean_rstd(const double* sums, const double* cs1, int C1, const double* cs2, int C2, int NB, int HW,
                               int groups, float eps, float* mean_rstd, void* stream);
 int b200_group_norm_bwd_sums(const void* x, int in_f32, int Cx, int c_off, int Ctot, const void* dy, int NB, int HW,

@@ -30,6 +30,8 @@ def tap_conv(x_nhwc, wp, cout, taps, stride=1, out_hw=None, x2=None):
 
 
 def _act(r, act):
+    if act == ops.ACT_EXP2:
+        return torch.exp2(r)
     if act == ops.ACT_SILU:
         return F.silu(r)
     if act == ops.ACT_GELU:
@@ -52,7 +54,7 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ops.ACT_
     wf = w.float() if w_t else w.float().transpose(-1, -2)
     r = af @ wf * alpha
     if bias is not None:
-        r = r + (bias[:, None] if bias_row else bias)
+        r = r + (bias.unsqueeze(-1) if bias_row else bias)
     if residual is not None:
         r = r * residual.float() if res_mul else r + residual.float()
     r = _act(r, act)
@@ -159,7 +161,12 @@ def layer_norm_bwd(x, dy, gamma, eps=1e-5, add=None, out_dtype=F32, dgamma=None,
     return dx.to(out_dtype), dg, db
 
 
-def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None):
+def rowdot_heads(a, c, heads):
+    B, L = a.shape[0], a.shape[1]
+    return (a[..., :heads * 64].float() * c[..., :heads * 64].float()).view(B, L, heads, 64).sum(-1).permute(0, 2, 1).contiguous()
+
+
+def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None, want_lse=False):
     B, Lq = q.shape[0], q.shape[1]
     if kv_segments == 2:                                   # batch b sees the keys of b % (B/2) then b % (B/2) + B/2
         h = B // 2
@@ -170,11 +177,14 @@ def attention_d64(q, k, v, heads, scale, kv_segments=1, out=None):
         return t.float().unflatten(-1, (heads, 64)).transpose(1, 2)
     k = k.expand(B, -1, -1) if k.shape[0] == 1 else k
     v = v.expand(B, -1, -1) if v.shape[0] == 1 else v
-    o = torch.softmax(split(q) @ split(k).transpose(-1, -2) * scale, dim=-1) @ split(v)
+    logits = split(q) @ split(k).transpose(-1, -2) * scale
+    o = torch.softmax(logits, dim=-1) @ split(v)
     o = o.transpose(1, 2).reshape(B, Lq, heads * 64).half()
     if out is not None:
         out.copy_(o)
-        return out
+        o = out
+    if want_lse:
+        return o, (torch.logsumexp(logits, dim=-1) * 1.4426950408889634).contiguous()      # log2 domain, [B, heads, Lq]
     return o
 
 
@@ -404,7 +414,7 @@ def upsample_nearest_bwd(dy, in_hw, add=None):
 
 _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm_mean_rstd=group_norm_mean_rstd,
                  group_norm_bwd=group_norm_bwd, layer_norm=layer_norm, layer_norm_bwd=layer_norm_bwd,
-                 attention_d64=attention_d64, softmax_rows=softmax_rows, softmax_bwd_rows=softmax_bwd_rows,
+                 attention_d64=attention_d64, rowdot_heads=rowdot_heads, softmax_rows=softmax_rows, softmax_bwd_rows=softmax_bwd_rows,
                  gather_planar=gather_planar, col_sum=col_sum, act_bwd=act_bwd, geglu_bwd=geglu_bwd,
                  softmax_groups=softmax_groups, cast_f16=cast_f16, im2col3x3=im2col3x3, conv3x3_small_cout=conv3x3_small_cout,
                  timestep_embedding=timestep_embedding, nhwc_to_nchw_f32=nhwc_to_nchw_f32,

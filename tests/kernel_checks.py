@@ -267,6 +267,33 @@ def check_conv_halo_taps(seed=91):
     return worst, 3e-5
 
 
+def check_attention_lse_and_rowdot(B=2, heads=5, Lq=300, Lk=200, seed=95):
+    """Flash kernel's log2-domain log-sum-exp output and the rowdot kernel (the two row statistics of the attention
+    backward) against torch; then P recomputed by the exp2-epilogue GEMM against softmax."""
+    C = heads * 64
+    q, k, v = _rand(B, Lq, C, seed=seed), _rand(B, Lk, C, seed=seed + 1), _rand(B, Lk, C, seed=seed + 2)
+    scale = 64 ** -0.5
+    o, lse = ops.attention_d64(q, k, v, heads, scale, want_lse=True)
+    def split(t):
+        return t.float().view(t.shape[0], t.shape[1], heads, 64).permute(0, 2, 1, 3)
+    logits = split(q) @ split(k).transpose(-1, -2) * scale
+    lse_ref = torch.logsumexp(logits, -1) * 1.4426950408889634
+    e1 = (lse - lse_ref).abs().max().item() / lse_ref.abs().max().item()
+    do = _rand(B, Lq, C, seed=seed + 3)
+    d = ops.rowdot_heads(do, o, heads)
+    d_ref = (split(do) * split(o)).sum(-1)
+    e2 = rel_l2(d, d_ref)
+    b = 1
+    qh = q[b].unflatten(-1, (heads, 64)).permute(1, 0, 2)
+    kh = k[b].unflatten(-1, (heads, 64)).permute(1, 0, 2)
+    p = torch.empty((heads, Lq, (Lk + 7) // 8 * 8), dtype=torch.float16, device=DEV)
+    ops.linear(qh, kh, bias=(-lse[b]).contiguous(), bias_row=True, act=ops.ACT_EXP2, alpha=scale * 1.4426950408889634,
+               out=p[:, :, :Lk])
+    torch.cuda.synchronize()
+    e3 = rel_l2(p[:, :, :Lk], torch.softmax(logits[b], -1))
+    return max(e1 / 1e-5, e2 / 1e-5, e3 / 1e-3) * 1e-3, 1e-3
+
+
 def check_upsample_conv_phases(NB=2, H=12, W=10, C=128, seed=21):
     """Upsample2D: nearest x2 + conv3x3 computed as four 2x2 convs on the low-res input."""
     from diffusion_e2e_ft_b200.modules import Upsample2D
@@ -711,6 +738,7 @@ CHECKS = {
     "attn_cross_2": lambda: check_attention(Lq=576, Lk=2),
     "attn_cross_77": lambda: check_attention(Lq=300, Lk=77),
     "attn_joint": lambda: check_attention(B=4, heads=5, Lq=576, joint=True),
+    "attn_lse_rowdot_exp2_gemm": check_attention_lse_and_rowdot,
     "upsample_2x": check_upsample,
     "upsample_size_f32": lambda: check_upsample(True, (15, 20)),
     "timestep_embedding": check_timestep_embedding,

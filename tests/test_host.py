@@ -29,7 +29,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
 def test_c_abi_rejects_bad_arguments_without_launching():
     from diffusion_e2e_ft_b200 import lib
     L = lib.load()
-    rc = L.b200_linear(None, 0, 0, None, 0, 0, 1, 1, 1, 1, None, 0, None, 0, 0, None, 0, 0, 0, 0, 1.0, None, 0, None, 0, 0, 0, None)
+    rc = L.b200_linear(None, 0, 0, None, 0, 0, 1, 1, 1, 1, None, 0, None, 0, 0, None, 0, 0, 0, 0, 1.0, None, 0, None, 0, 0, 0, 0, None)
     assert rc < 0 and b"null pointer" in L.b200_last_error_string()
     rc = L.b200_layer_norm(1, 0, 10, 12, 1, 1, 1e-5, 1, None)       # C not a multiple of 8
     assert rc < 0 and b"multiple of 8" in L.b200_last_error_string()
