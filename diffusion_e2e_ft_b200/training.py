@@ -64,6 +64,38 @@ def e2e_ft_loss(unet, vae, scheduler, rgb, ground_truth, val_mask, empty_encodin
     return ab.task_loss(est, ground_truth, val_mask, normals), est
 
 
+def e2e_ft_loss_geowizard(unet, vae, scheduler, rgb, depth_gt, normal_gt, val_mask, img_embed, domain="indoor",
+                          depth_scale=0.5, normal_scale=1.0):
+    """Differentiable joint depth + normal micro-step of the GeoWizard recipe
+    (GeoWizard/geowizard/training/train_depth_normal.py:640-766, `--e2e_ft`, zeros noise): one UNet call on the
+    [depth x B | normal x B] batch with the hybrid class embedding and joint self-attention, x0 by the v-prediction closed
+    form, ONE decoder pass over both halves, depth = clamp(mean_c), normals = clamp(x / (|x| + 1e-5)),
+    loss = depth_scale * SSI(depth) + normal_scale * angular(normals, -normal_gt)   (the reference trains on inverted
+    normals, :742).  rgb [B,3,H,W], depth_gt [B,1,H,W], normal_gt [B,3,H,W], val_mask [B,1,H,W] bool, img_embed
+    [B,1,768] (CLIP image embedding).  Returns (loss, depth_estimate, normal_estimate)."""
+    from . import autograd_blocks as ab
+    from .pipelines import DepthNormalEstimationPipeline
+    B = rgb.shape[0]
+    dev = rgb.device
+    with torch.no_grad():
+        rgb_latents = vae.encode_scaled_mean(rgb)
+    T = scheduler.config["num_train_timesteps"]
+    t = T - 1                                                                             # :646-648
+    timesteps = torch.full((2 * B,), t, device=dev, dtype=torch.long)
+    x = torch.cat((rgb_latents.repeat(2, 1, 1, 1), torch.zeros_like(rgb_latents).repeat(2, 1, 1, 1)), dim=1)   # :705
+    ctx = img_embed.to(dev).repeat(2, 1, 1)                                               # :683
+    cls = DepthNormalEstimationPipeline.class_embedding(domain, B, dev, rgb_latents.dtype)                   # :686-703
+    pred = unet(x, timesteps, ctx, class_labels=cls, return_dict=False)[0]
+    a_t = float(scheduler.alphas_cumprod[t])
+    assert scheduler.config["prediction_type"] == "v_prediction"
+    dec = vae.decode_from_prediction(pred, -math.sqrt(1.0 - a_t))                         # :722-737, one decoder pass
+    est_d = ab.decode_post(dec[:B].contiguous(), False)                                   # :739-741
+    est_n = ab.decode_post(dec[B:].contiguous(), True)                                    # :743-746
+    loss_d = ab.task_loss(est_d, depth_gt, val_mask, False)
+    loss_n = ab.task_loss(est_n, -normal_gt, val_mask, True)
+    return depth_scale * loss_d + normal_scale * loss_n, est_d, est_n
+
+
 def allreduce_mean_(flat_grad, group=None):
     """DDP gradient exchange of the fine-tuning step (training/train.py:470,563 via accelerate): one all-reduce
     of the flat gradient buffer over the data-parallel ranks, averaged.  NCCL over NVLink on the GPU box, gloo

@@ -190,15 +190,22 @@ class Conv1x1Small(nn.Conv2d):
 
     def forward(self, x, scale_in=1.0, x2=None, scale_in2=0.0, rows=None, scale_out=1.0):
         _check_input(x, "B200AutoencoderKL.(post_)quant_conv")
-        w = self.weight.detach().reshape(self.out_channels, self.in_channels).to(F32)
-        b = self.bias.detach().to(F32)
-        if rows is not None:
-            w, b = w[:rows], b[:rows]
-        if scale_out != 1.0:
-            w, b = w * scale_out, b * scale_out
+        # the (row-sliced, pre-scaled) fp32 matrix is derived once per weights version, not per call
+        cache = self.__dict__.setdefault("_wb_cache", {})
+        pk = cache.setdefault((rows, float(scale_out)), Packed())
+
+        def build():
+            w = self.weight.detach().reshape(self.out_channels, self.in_channels).to(F32)
+            b = self.bias.detach().to(F32)
+            if rows is not None:
+                w, b = w[:rows], b[:rows]
+            if scale_out != 1.0:
+                w, b = w * scale_out, b * scale_out
+            return w.contiguous(), b.contiguous()
+        w, b = pk.get([self.weight, self.bias], build)
         xin = x if x.dtype == F32 else x.float()
         x2in = None if x2 is None else (x2 if x2.dtype == F32 else x2.float())
-        out = ops.pointwise_nchw(xin.contiguous(), scale_in, w.contiguous(), b.contiguous(),
+        out = ops.pointwise_nchw(xin.contiguous(), scale_in, w, b,
                                  in2=None if x2in is None else x2in.contiguous(), a2=scale_in2,
                                  cin=self.in_channels)
         return out if out.dtype == x.dtype else out.to(x.dtype)

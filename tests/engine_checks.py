@@ -373,3 +373,55 @@ def run_checkpointing_tiny(device="cuda:0"):
         den_o += ref[n].grad.pow(2).sum().item()
     return dict(global_rel_diff=(num / den) ** 0.5, worst_rel_diff=worst, worst_name=worst_name,
                 ckpt_vs_oracle_global=(num_o / den_o) ** 0.5)
+
+
+def run_training_step_geowizard_tiny(device="cuda:0"):
+    """GeoWizard joint depth + normal micro-step (train_depth_normal.py:640-766): engine `e2e_ft_loss_geowizard` +
+    backward vs torch.autograd through the fp32 oracle graph (joint attention, class-embedding projection, one decoder
+    pass over both halves, 0.5 * SSI + angular on inverted normals)."""
+    from diffusion_e2e_ft_b200.training import LOSS_SCALE, e2e_ft_loss_geowizard
+    gunet_ref, vae_ref = MG.build_tiny("geowizard")
+    unet, vae = engine_from_oracle(gunet_ref, vae_ref, device)
+    unet.requires_grad_(True)
+    gunet_ref.requires_grad_(True)
+    vae_ref.requires_grad_(False)
+    g = torch.Generator().manual_seed(17)
+    B = 2
+    rgb = torch.rand(B, 3, 64, 64, generator=g) * 2 - 1
+    emb = torch.randn(B, 1, 96, generator=g) * 0.5
+    mask = torch.rand(B, 1, 64, 64, generator=g) > 0.2
+    gt_d = torch.rand(B, 1, 64, 64, generator=g) * 9.9 + 0.1
+    gt_n = torch.nn.functional.normalize(torch.randn(B, 3, 64, 64, generator=g), dim=1)
+    sched_o = OP.DDIMOneStep()
+    with torch.no_grad():
+        lat = OP.encode_rgb(vae_ref, rgb)
+    x = torch.cat([lat.repeat(2, 1, 1, 1), torch.zeros_like(lat).repeat(2, 1, 1, 1)], 1)
+    cls = OP.geowizard_class_embedding("indoor", rgb.dtype, B)
+    v = gunet_ref(x, torch.full((2 * B,), 999), encoder_hidden_states=emb.repeat(2, 1, 1), class_labels=cls).sample
+    dec = OP.decode_latent(vae_ref, sched_o.pred_original_sample(v, 999, torch.zeros_like(v)))
+    est_d = dec[:B].mean(1, keepdim=True).clamp(-1, 1)
+    est_n = (dec[B:] / (dec[B:].norm(dim=1, keepdim=True) + 1e-5)).clamp(-1, 1)
+    want = 0.5 * OP.ssi_loss(est_d, gt_d, mask) + OP.angular_loss(est_n, -gt_n, mask)
+    want.backward()
+    got, _, _ = e2e_ft_loss_geowizard(unet, vae, DDIMScheduler(), rgb.to(device), gt_d.to(device), gt_n.to(device),
+                                      mask.to(device), emb.to(device), "indoor")
+    (got * LOSS_SCALE).backward()
+    ref = dict(gunet_ref.named_parameters())
+    num = den = 0.0
+    worst, worst_name, missing = 0.0, None, []
+    for n, p in unet.named_parameters():
+        if p.grad is None:
+            missing.append(n)
+            continue
+        ge, gr = p.grad.detach().float().cpu() / LOSS_SCALE, ref[n].grad
+        num += (ge - gr).pow(2).sum().item()
+        den += gr.pow(2).sum().item()
+    for n, p in unet.named_parameters():
+        if p.grad is None:
+            continue
+        gr = ref[n].grad
+        e = rel_l2(p.grad.detach().float().cpu() / LOSS_SCALE, gr)
+        if e > worst and gr.norm() > 1e-3 * den ** 0.5:
+            worst, worst_name = e, n
+    return dict(loss_engine=got.item(), loss_oracle=want.item(), loss_rel=abs(got.item() - want.item()) / abs(want.item()),
+                grad_global=(num / den) ** 0.5, grad_worst=worst, worst_name=worst_name, missing=missing)

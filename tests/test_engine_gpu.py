@@ -187,3 +187,16 @@ def test_wgrad_variants(padded, split):
         assert not r["missing"] and r["grad_global"] <= 1e-2 and r["grad_worst"] <= 2e-2, r
     finally:
         bw.WGRAD_PADDED, bw.WGRAD_SPLIT_K, bw.WGRAD_MIN_KBLOCKS = keep
+
+
+@pytest.mark.gpu
+def test_geowizard_joint_depth_normal_training_step():
+    """GeoWizard/geowizard/training/train_depth_normal.py:640-766 (`--e2e_ft`): joint depth + normal micro-step on the
+    engine (`training.e2e_ft_loss_geowizard`) — loss and UNet parameter gradients vs torch.autograd through the fp32
+    oracle.  Same tolerance class as the normals micro-step (non-smooth angular loss, fp16 operands through the VAE
+    decoder backward as well)."""
+    r = EC.run_training_step_geowizard_tiny()
+    print(r)
+    assert not r["missing"], r["missing"]
+    assert r["loss_rel"] <= 3e-3, r
+    assert r["grad_global"] <= 6e-2 and r["grad_worst"] <= 0.2, r

@@ -38,6 +38,14 @@ def test_training_micro_step_wiring(emulated, modality, tol):
     assert r["grad_global"] <= tol and r["grad_worst"] <= 3 * tol, r
 
 
+def test_geowizard_joint_training_step_wiring(emulated):
+    """train_depth_normal.py:640-766 on the engine (kernels emulated): joint depth + normal loss and its backward."""
+    r = EC.run_training_step_geowizard_tiny(device="cpu")
+    assert not r["missing"], r["missing"]
+    assert r["loss_rel"] <= 3e-3, r
+    assert r["grad_global"] <= 6e-2 and r["grad_worst"] <= 0.2, r
+
+
 def test_training_loop_wiring(emulated):
     """flat parameter / gradient buffers, loss scaling, packed-weight cache invalidation after the optimizer step"""
     from test_engine_gpu import _check_loop
