@@ -425,3 +425,24 @@ def run_training_step_geowizard_tiny(device="cuda:0"):
             worst, worst_name = e, n
     return dict(loss_engine=got.item(), loss_oracle=want.item(), loss_rel=abs(got.item() - want.item()) / abs(want.item()),
                 grad_global=(num / den) ** 0.5, grad_worst=worst, worst_name=worst_name, missing=missing)
+
+
+@torch.no_grad()
+def run_batch_consistency(device="cuda:0", res=384, batch=16):
+    """bs-16 normals inference (BASELINE.json configs[4]) vs the same images one by one (random SD-2-width weights)."""
+    torch.manual_seed(7)
+    with torch.device(device):
+        unet = B200UNet2DConditionModel()
+        vae = B200AutoencoderKL()
+    unet.half().eval().requires_grad_(False)
+    vae.half().eval().requires_grad_(False)
+    ete = (torch.randn(1, 2, 1024, device=device) * 0.5).half()
+    pipe = MarigoldPipeline(unet, vae, DDIMScheduler(), empty_text_embed=ete)
+    g = torch.Generator().manual_seed(11)
+    rgb = (torch.rand(batch, 3, res, res, generator=g) * 2 - 1).to(device)
+    full = pipe.single_infer(rgb, 1, False, noise="zeros", normals=True)
+    worst = 0.0
+    for i in (0, batch // 2, batch - 1):
+        one = pipe.single_infer(rgb[i:i + 1], 1, False, noise="zeros", normals=True)
+        worst = max(worst, rel_l2(full[i:i + 1], one))
+    return dict(worst_vs_single=worst, norm_err=(full.float().norm(dim=1) - 1).abs().max().item())

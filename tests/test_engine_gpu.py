@@ -80,6 +80,9 @@ def test_full_size_768_against_fp32_oracle_on_gpu():
     print(r)
     for k in ("rgb_latent_rel_l2", "unet_rel_l2", "decode_rel_l2", "depth_rel_l2"):
         assert r[k] <= 3e-3, (k, r)
+    # the END-TO-END depth map is inside the contract's 1e-3 at full size (measured 9.7e-4, profiles/parity_r02.json);
+    # locked in with a margin for box-to-box atomics / clock noise.  The intermediate stages are not.
+    assert r["depth_rel_l2"] <= 1.3e-3, r
     assert r["absrel_delta"] <= 1e-3, r
     assert 0.0 <= r["depth_min"] and r["depth_max"] <= 1.0, r
     assert r["normals_norm_err"] <= 2e-3, r
@@ -200,3 +203,18 @@ def test_geowizard_joint_depth_normal_training_step():
     assert not r["missing"], r["missing"]
     assert r["loss_rel"] <= 3e-3, r
     assert r["grad_global"] <= 6e-2 and r["grad_worst"] <= 0.2, r
+
+
+@pytest.mark.gpu
+def test_full_size_1024_and_batch16_consistency():
+    """BASELINE.json configs[4] corners: 1024x1024 (latent 128^2, self-attention over 16384 tokens) against the fp32
+    oracle on the same GPU, and a batch of 16 at 384x384 whose every image must equal its batch-1 result (the halo /
+    swapped tile choices and the fused per-image statistics all depend on the batch size)."""
+    r = EC.run_full_size(res=1024, batch=1)
+    print(r)
+    for k in ("rgb_latent_rel_l2", "unet_rel_l2", "decode_rel_l2", "depth_rel_l2"):
+        assert r[k] <= 3e-3, (k, r)
+    assert r["absrel_delta"] <= 1e-3 and r["normals_norm_err"] <= 2e-3 and r["batch_consistency"] <= 1e-3, r
+    c = EC.run_batch_consistency(res=384, batch=16)
+    print(c)
+    assert c["worst_vs_single"] <= 1.5e-3, c
