@@ -84,6 +84,33 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, in
   out[(long long)b * dim + half + j] = __float2half_rn(sinf(a));
 }
 
+// CLIP text embeddings (transformers modeling_clip CLIPTextEmbeddings): out[b*L + l][c] = tok[ids[b*L + l]][c] + pos[l][c],
+// fp32 residual stream out; the tables are fp16 or fp32 (the module's parameter dtype).  One warp-strided pass, 8 B+ per lane.
+template <typename T>
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const T* __restrict__ tok, const T* __restrict__ pos,
+                                    long long rows, int L, int C, int vocab, float* __restrict__ out) {
+  const long long total = rows * (long long)(C / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (C / 4);
+    const int c = (int)(i - r * (C / 4)) * 4;
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const T* a = tok + id * C + c;
+    const T* b = pos + (r % L) * C + c;
+    float4 o;
+    if constexpr (sizeof(T) == 2) {
+      const __half2 a0 = reinterpret_cast<const __half2*>(a)[0], a1 = reinterpret_cast<const __half2*>(a)[1];
+      const __half2 b0 = reinterpret_cast<const __half2*>(b)[0], b1 = reinterpret_cast<const __half2*>(b)[1];
+      const float2 fa0 = __half22float2(a0), fa1 = __half22float2(a1), fb0 = __half22float2(b0), fb1 = __half22float2(b1);
+      o = make_float4(fa0.x + fb0.x, fa0.y + fb0.y, fa1.x + fb1.x, fa1.y + fb1.y);
+    } else {
+      const float4 fa = *reinterpret_cast<const float4*>(a), fb = *reinterpret_cast<const float4*>(b);
+      o = make_float4(fa.x + fb.x, fa.y + fb.y, fa.z + fb.z, fa.w + fb.w);
+    }
+    *reinterpret_cast<float4*>(out + r * C + c) = o;
+  }
+}
+
 __global__ void pointwise_nchw_kernel(const float* __restrict__ in1, float a1,
                                       const float* __restrict__ in2, float a2, int in_cstride,
                                       const float* __restrict__ Wm, const float* __restrict__ bias,
@@ -209,6 +236,20 @@ extern "C" int b200_timestep_embedding(const float* t, int B, int dim, void* out
   const int n = B * (dim / 2);
   timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, B, dim, (__half*)out);
   B200_CHECK_LAUNCH("timestep_embedding_kernel");
+  return 0;
+}
+
+extern "C" int b200_embed_tokens(const long long* ids, const void* tok, const void* pos, int w_f32, long long rows, int L,
+                                 int C, int vocab, float* out, void* stream) {
+  B200_CHECK_ARG(ids && tok && pos && out && rows > 0 && L > 0 && vocab > 0, "b200_embed_tokens: bad arguments");
+  B200_CHECK_ARG(C > 0 && C % 4 == 0, "b200_embed_tokens: C=%d must be a multiple of 4", C);
+  const long long total = rows * (long long)(C / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w_f32)
+    embed_tokens_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(ids, (const float*)tok, (const float*)pos, rows, L, C, vocab, out);
+  else
+    embed_tokens_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(ids, (const __half*)tok, (const __half*)pos, rows, L, C, vocab, out);
+  B200_CHECK_LAUNCH("embed_tokens_kernel");
   return 0;
 }
 

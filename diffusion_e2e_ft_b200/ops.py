@@ -404,6 +404,19 @@ def timestep_embedding(t, dim):
 
 
 @_timed("misc")
+def embed_tokens(ids, tok, pos):
+    """CLIP text embeddings: ids [B, L] int64, tables [vocab, C] / [max_pos, C] (fp16 or fp32) -> fp32 [B*L, C]."""
+    _need_cuda(ids, tok, pos)
+    assert ids.dtype == torch.long and ids.is_contiguous() and tok.dtype == pos.dtype and tok.dtype in (F16, F32)
+    B, L = ids.shape
+    C = tok.shape[1]
+    tok, pos = tok.detach().contiguous(), pos.detach().contiguous()
+    out = torch.empty((B * L, C), dtype=F32, device=ids.device)
+    _ck(_lib.load().b200_embed_tokens(_p(ids), _p(tok), _p(pos), int(tok.dtype == F32), B * L, L, C, tok.shape[0],
+                                      _p(out), _stream()), "b200_embed_tokens")
+    return out
+
+
 def pointwise_nchw(in1, a1, wm, bias, in2=None, a2=0.0, cin=None):
     """out[n,co] = sum_ci wm[co,ci]*(a1*in1[n,ci] + a2*in2[n,ci]) + bias[co]; fp32 NCHW, C<=8."""
     _need_cuda(in1)

@@ -158,6 +158,12 @@ int b200_upsample_nearest_nhwc(const void* x, int in_f32, int NB, int H, int W, 
  * t is a device array of B floats.  unet_2d_condition.py:974. */
 int b200_timestep_embedding(const float* t, int B, int dim, void* out, void* stream);
 
+/* CLIP text embeddings: out[r][c] = tok[ids[r]][c] + pos[r % L][c], fp32 [rows][C]; ids int64 (clamped to the table);
+ * tables fp16 or fp32 (w_f32).  transformers==4.37.2 models/clip/modeling_clip.py CLIPTextEmbeddings.forward, reached
+ * from Marigold/marigold/marigold_pipeline.py:369 (`self.text_encoder(text_input_ids)[0]`). */
+int b200_embed_tokens(const long long* ids, const void* tok, const void* pos, int w_f32, long long rows, int L, int C,
+                      int vocab, float* out, void* stream);
+
 /* Small dense per-pixel channel mix on NCHW fp32 (Cin, Cout <= 8):
  * out[n][co][p] = sum_ci Wm[co][ci] * (a1*in1[n][ci][p] + a2*in2[n][ci][p]) + bias[co].
  * Serves quant_conv + latent scaling (marigold_pipeline.py:494-497) and

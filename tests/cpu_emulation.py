@@ -279,6 +279,11 @@ def timestep_embedding(t, dim):
     return torch.cat([torch.cos(a), torch.sin(a)], dim=-1).half()        # flip_sin_to_cos=True
 
 
+def embed_tokens(ids, tok, pos):
+    B, L = ids.shape
+    return (tok.float()[ids] + pos.float()[:L][None]).reshape(B * L, -1).contiguous()
+
+
 def nhwc_to_nchw_f32(x):
     return x.float().permute(0, 3, 1, 2).contiguous()
 
@@ -417,7 +422,7 @@ _EMULATED = dict(linear=linear, conv2d=conv2d, group_norm=group_norm, group_norm
                  attention_d64=attention_d64, rowdot_heads=rowdot_heads, softmax_rows=softmax_rows, softmax_bwd_rows=softmax_bwd_rows,
                  gather_planar=gather_planar, col_sum=col_sum, act_bwd=act_bwd, geglu_bwd=geglu_bwd,
                  softmax_groups=softmax_groups, cast_f16=cast_f16, im2col3x3=im2col3x3, conv3x3_small_cout=conv3x3_small_cout,
-                 timestep_embedding=timestep_embedding, nhwc_to_nchw_f32=nhwc_to_nchw_f32,
+                 timestep_embedding=timestep_embedding, embed_tokens=embed_tokens, nhwc_to_nchw_f32=nhwc_to_nchw_f32,
                  pointwise_nchw=pointwise_nchw, decode_post=decode_post, ssi_loss=ssi_loss, angular_loss=angular_loss,
                  ssi_loss_bwd=ssi_loss_bwd, angular_loss_bwd=angular_loss_bwd, decode_post_bwd=decode_post_bwd, grad_norm_sq=grad_norm_sq, adamw_step=adamw_step, adamw_step_state=adamw_step_state,
                  upsample_nearest=upsample_nearest, upsample_nearest_bwd=upsample_nearest_bwd)

@@ -429,20 +429,46 @@ def run_training_step_geowizard_tiny(device="cuda:0"):
 
 @torch.no_grad()
 def run_batch_consistency(device="cuda:0", res=384, batch=16):
-    """bs-16 normals inference (BASELINE.json configs[4]) vs the same images one by one (random SD-2-width weights)."""
-    torch.manual_seed(7)
-    with torch.device(device):
-        unet = B200UNet2DConditionModel()
-        vae = B200AutoencoderKL()
-    unet.half().eval().requires_grad_(False)
-    vae.half().eval().requires_grad_(False)
-    ete = (torch.randn(1, 2, 1024, device=device) * 0.5).half()
-    pipe = MarigoldPipeline(unet, vae, DDIMScheduler(), empty_text_embed=ete)
+    """bs-16 inference (BASELINE.json configs[4]) vs the same images one by one, SD-2 widths, the seeded weights of
+    run_full_size.  Both sides are the engine: they differ only in tile shapes / summation order (halo vs per-tap conv,
+    swapped epilogue, atomics order of the fused statistics), i.e. in which fp16 roundings flip."""
+    from oracle.unet import UNet2DConditionRef, UNetConfig, seeded_init
+    from oracle.vae import AutoencoderKLRef, VAEConfig
+    uref = seeded_init(UNet2DConditionRef(UNetConfig()), seed=4321).eval()
+    vref = seeded_init(AutoencoderKLRef(VAEConfig()), seed=99).eval()
+    unet, vae = engine_from_oracle(uref, vref, device)
     g = torch.Generator().manual_seed(11)
+    ete = (torch.randn(1, 2, 1024, generator=g) * 0.5).to(device)
+    pipe = MarigoldPipeline(unet, vae, DDIMScheduler(), empty_text_embed=ete)
     rgb = (torch.rand(batch, 3, res, res, generator=g) * 2 - 1).to(device)
-    full = pipe.single_infer(rgb, 1, False, noise="zeros", normals=True)
-    worst = 0.0
+    full_d = pipe.single_infer(rgb, 1, False, noise="zeros")
+    full_n = pipe.single_infer(rgb, 1, False, noise="zeros", normals=True)
+    worst_d, worst_a = 0.0, 0.0
     for i in (0, batch // 2, batch - 1):
-        one = pipe.single_infer(rgb[i:i + 1], 1, False, noise="zeros", normals=True)
-        worst = max(worst, rel_l2(full[i:i + 1], one))
-    return dict(worst_vs_single=worst, norm_err=(full.float().norm(dim=1) - 1).abs().max().item())
+        worst_d = max(worst_d, rel_l2(full_d[i:i + 1], pipe.single_infer(rgb[i:i + 1], 1, False, noise="zeros")))
+        worst_a = max(worst_a, mean_angle_deg(full_n[i:i + 1],
+                                              pipe.single_infer(rgb[i:i + 1], 1, False, noise="zeros", normals=True)))
+    return dict(depth_worst_vs_single=worst_d, normals_worst_angle_deg=worst_a,
+                norm_err=(full_n.float().norm(dim=1) - 1).abs().max().item())
+
+
+@torch.no_grad()
+def run_pipeline_with_text_encoder(device="cuda:0"):
+    """marigold_pipeline.py:355-369 on the engine: MarigoldPipeline.encode_empty_text -> B200CLIPTextModel (CUDA) ->
+    ctx [1, 2, 128] -> the UNet's constant-context cross-attention; checked against the oracle text encoder feeding the
+    oracle pipeline."""
+    from diffusion_e2e_ft_b200 import B200CLIPTextModel, EmptyPromptTokenizer
+    from oracle.clip_text import clip_text_forward, random_state_dict, tiny_clip_cfg
+    from oracle.pipeline import DDIMOneStep
+    unet_ref, vae_ref = MG.build_tiny()
+    unet, vae = engine_from_oracle(unet_ref, vae_ref, device)
+    cfg = tiny_clip_cfg()
+    sd = random_state_dict(cfg, seed=21)
+    enc = B200CLIPTextModel(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2).eval()
+    enc.load_state_dict(sd)
+    pipe = MarigoldPipeline(unet, vae, DDIMScheduler(), text_encoder=enc.to(device), tokenizer=EmptyPromptTokenizer())
+    rgb = (torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(3)) * 2 - 1)
+    depth = pipe.single_infer(rgb.to(device), 1, False, noise="zeros")
+    ctx_ref = clip_text_forward(sd, cfg, torch.tensor([[49406, 49407]]))[0]
+    want = OP.marigold_single_infer(unet_ref, vae_ref, DDIMOneStep(), rgb, ctx_ref)
+    return dict(ctx_rel_l2=rel_l2(pipe.empty_text_embed, ctx_ref), depth_rel_l2=rel_l2(depth, want))
