@@ -11,6 +11,7 @@ from .vae import B200AutoencoderKL  # noqa: F401
 from .pipelines import (DDIMScheduler, MarigoldPipeline, MarigoldDepthOutput,  # noqa: F401
                         DepthNormalEstimationPipeline, DepthNormalPipelineOutput, pyramid_noise_like)
 from .clip_text import B200CLIPTextModel, EmptyPromptTokenizer  # noqa: F401
+from .clip_vision import B200CLIPVisionModelWithProjection, CLIPImageProcessorConfig  # noqa: F401
 from .ensemble import ensemble_normals, ensemble_normals_with_index, ensemble_depths  # noqa: F401
 
 __version__ = "0.1.0"

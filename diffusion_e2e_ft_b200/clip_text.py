@@ -13,8 +13,8 @@ the flash kernel, one launch per query position with that position's key prefix 
 empty prompt, 77 at most, and the encoder runs once per process) -> out_proj GEMM + residual -> LayerNorm -> fc1 GEMM
 with the erf-GELU epilogue -> fc2 GEMM + residual] -> final LayerNorm.  No torch arithmetic; no CPU fallback.
 
-Not built: `quick_gelu` checkpoints (SD-1.x text encoders; the SD-2 encoder both fine-tuned models ship uses "gelu"),
-heads whose width is not 64, and the CLIP *vision* tower GeoWizard conditions on (head_dim 80) — DESIGN.md §8.
+`quick_gelu` towers (OpenAI CLIP: SD-1.x text encoders, the ViT-L/14 image encoder of clip_vision.py) run on the SiLU
+epilogue with pre-scaled fc1 weights.  Not built: heads whose width is not 64.
 """
 import json
 import os
@@ -63,17 +63,26 @@ class _MLP(nn.Module):
         self.fc1, self.fc2 = nn.Linear(C, I), nn.Linear(I, C)
 
 
+QUICK_GELU_K = 1.702
+
+
 class _EncoderLayer(nn.Module):
-    def __init__(self, C, I, eps):
+    """transformers CLIPEncoderLayer (pre-LN).  `act`: "gelu" -> the erf-GELU GEMM epilogue; "quick_gelu"
+    (x * sigmoid(1.702 x), the OpenAI CLIP towers) -> the SiLU epilogue on fc1 weights / bias pre-scaled by 1.702
+    (silu(1.702 z) = 1.702 * quick_gelu(z)), undone exactly by alpha = 1 / 1.702 on the fc2 accumulator."""
+
+    def __init__(self, C, I, eps, act="gelu"):
         super().__init__()
         self.self_attn = _SelfAttn(C)
         self.layer_norm1 = nn.LayerNorm(C, eps=eps)
         self.mlp = _MLP(C, I)
         self.layer_norm2 = nn.LayerNorm(C, eps=eps)
+        self.eps, self.act = eps, act
         self._pk = Packed()
 
     def packed(self):
         a, m = self.self_attn, self.mlp
+        k = QUICK_GELU_K if self.act == "quick_gelu" else 1.0
 
         def build():
             return dict(ln1=(_f32(self.layer_norm1.weight), _f32(self.layer_norm1.bias)),
@@ -81,8 +90,30 @@ class _EncoderLayer(nn.Module):
                         wqkv=_f16(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
                         bqkv=_f32(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)),
                         wo=_f16(a.out_proj.weight), bo=_f32(a.out_proj.bias),
-                        w1=_f16(m.fc1.weight), b1=_f32(m.fc1.bias), w2=_f16(m.fc2.weight), b2=_f32(m.fc2.bias))
+                        w1=_f16(m.fc1.weight.float() * k), b1=_f32(m.fc1.bias.float() * k),
+                        w2=_f16(m.fc2.weight), b2=_f32(m.fc2.bias))
         return self._pk.get(list(self.parameters()), build)
+
+    def run(self, h, B, L, heads, causal):
+        """h: fp32 residual stream [B*L, C] -> the same after this layer."""
+        pk = self.packed()
+        C = h.shape[1]
+        y = ops.layer_norm(h, *pk["ln1"], eps=self.eps)
+        qkv = ops.linear(y, pk["wqkv"], pk["bqkv"]).view(B, L, 3 * C)
+        if causal:
+            o = torch.empty((B, L, C), dtype=F16, device=h.device)
+            for i in range(L):                                   # query i sees keys 0..i
+                ops.attention_d64(qkv[:, i:i + 1, :C], qkv[:, :i + 1, C:2 * C], qkv[:, :i + 1, 2 * C:], heads, 0.125,
+                                  out=o[:, i:i + 1])
+        else:
+            o = ops.attention_d64(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, 0.125)
+        h = ops.linear(o.view(B * L, C), pk["wo"], pk["bo"], residual=h, out_dtype=F32)
+        y = ops.layer_norm(h, *pk["ln2"], eps=self.eps)
+        if self.act == "quick_gelu":
+            m = ops.linear(y, pk["w1"], pk["b1"], act=ops.ACT_SILU)
+            return ops.linear(m, pk["w2"], pk["b2"], residual=h, out_dtype=F32, alpha=1.0 / QUICK_GELU_K)
+        m = ops.linear(y, pk["w1"], pk["b1"], act=ops.ACT_GELU)
+        return ops.linear(m, pk["w2"], pk["b2"], residual=h, out_dtype=F32)
 
 
 class _Embeddings(nn.Module):
@@ -93,9 +124,9 @@ class _Embeddings(nn.Module):
 
 
 class _Encoder(nn.Module):
-    def __init__(self, n, C, I, eps):
+    def __init__(self, n, C, I, eps, act="gelu"):
         super().__init__()
-        self.layers = nn.ModuleList([_EncoderLayer(C, I, eps) for _ in range(n)])
+        self.layers = nn.ModuleList([_EncoderLayer(C, I, eps, act) for _ in range(n)])
 
 
 class _TextTransformer(nn.Module):
@@ -103,7 +134,8 @@ class _TextTransformer(nn.Module):
         super().__init__()
         C = cfg["hidden_size"]
         self.embeddings = _Embeddings(cfg["vocab_size"], C, cfg["max_position_embeddings"])
-        self.encoder = _Encoder(cfg["num_hidden_layers"], C, cfg["intermediate_size"], cfg["layer_norm_eps"])
+        self.encoder = _Encoder(cfg["num_hidden_layers"], C, cfg["intermediate_size"], cfg["layer_norm_eps"],
+                                cfg["hidden_act"])
         self.final_layer_norm = nn.LayerNorm(C, eps=cfg["layer_norm_eps"])
 
 
@@ -128,8 +160,8 @@ class B200CLIPTextModel(nn.Module):
         super().__init__()
         if hidden_size != 64 * num_attention_heads:
             raise NotImplementedError(f"head width {hidden_size // num_attention_heads}: the attention kernel is d=64")
-        if hidden_act != "gelu":
-            raise NotImplementedError(f"hidden_act={hidden_act!r}: only the erf-GELU epilogue exists (SD-2 text encoder)")
+        if hidden_act not in ("gelu", "quick_gelu"):
+            raise NotImplementedError(f"hidden_act={hidden_act!r}: gelu (SD-2) and quick_gelu (OpenAI CLIP) are built")
         self.config = ConfigDict(vocab_size=vocab_size, hidden_size=hidden_size, intermediate_size=intermediate_size,
                                  num_hidden_layers=num_hidden_layers, num_attention_heads=num_attention_heads,
                                  max_position_embeddings=max_position_embeddings, layer_norm_eps=layer_norm_eps,
@@ -211,19 +243,8 @@ class B200CLIPTextModel(nn.Module):
             raise ValueError(f"sequence length {L} > max_position_embeddings {cfg['max_position_embeddings']}")
         emb = self.text_model.embeddings
         h = ops.embed_tokens(ids, emb.token_embedding.weight, emb.position_embedding.weight)
-        scale = 64 ** -0.5
         for layer in self.text_model.encoder.layers:
-            pk = layer.packed()
-            y = ops.layer_norm(h, *pk["ln1"], eps=cfg["layer_norm_eps"])
-            qkv = ops.linear(y, pk["wqkv"], pk["bqkv"]).view(B, L, 3 * C)
-            o = torch.empty((B, L, C), dtype=F16, device=ids.device)
-            for i in range(L):                                   # causal: query i sees keys 0..i
-                ops.attention_d64(qkv[:, i:i + 1, :C], qkv[:, :i + 1, C:2 * C], qkv[:, :i + 1, 2 * C:], H, scale,
-                                  out=o[:, i:i + 1])
-            h = ops.linear(o.view(B * L, C), pk["wo"], pk["bo"], residual=h, out_dtype=F32)
-            y = ops.layer_norm(h, *pk["ln2"], eps=cfg["layer_norm_eps"])
-            m = ops.linear(y, pk["w1"], pk["b1"], act=ops.ACT_GELU)
-            h = ops.linear(m, pk["w2"], pk["b2"], residual=h, out_dtype=F32)
+            h = layer.run(h, B, L, H, causal=True)
         fl = self.text_model.final_layer_norm
         fin = self._pk.get([fl.weight, fl.bias], lambda: (_f32(fl.weight), _f32(fl.bias)))
         last16 = ops.layer_norm(h, *fin, eps=cfg["layer_norm_eps"]).view(B, L, C)

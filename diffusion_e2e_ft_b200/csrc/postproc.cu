@@ -242,15 +242,30 @@ __global__ void rgb_normalise_kernel(const T* __restrict__ x, long long n, int r
   }
 }
 
-// Separable resize along one axis with torch's antialiased-bilinear weights (aten upsample_bilinear2d_aa, align_corners
-// = False): for output index o, centre c = scale * (o + 0.5), support = max(scale, 1), taps x in
-// [floor(c - support + 0.5), floor(c + support + 0.5)) clipped to the input, weight triangle((x - c + 0.5) / max(scale, 1)),
-// normalised to sum 1.  With scale <= 1 (upsampling) this is plain bilinear interpolation.
+// Separable antialiased resize along one axis with torch's weights (aten upsample_{bilinear,bicubic}2d_aa, align_corners =
+// False): for output index o, centre c = scale * (o + 0.5), support = (interp_size / 2) * max(scale, 1) with interp_size 2
+// (triangle filter) or 4 (Keys cubic, a = -0.5), taps x in [floor(c - support + 0.5), floor(c + support + 0.5)) clipped to
+// the input, weight filter((x - c + 0.5) / max(scale, 1)), normalised to sum 1.
 // x: [planes][in_len][inner] -> out [planes][out_len][inner]  (inner = 1 for the width pass, = width for the height pass)
+template <bool CUBIC>
+__device__ __forceinline__ float aa_filter(float x) {
+  x = fabsf(x);
+  if constexpr (!CUBIC) {
+    return x < 1.0f ? 1.0f - x : 0.f;
+  } else {
+    const float a = -0.5f;
+    if (x < 1.0f) return ((a + 2.0f) * x - (a + 3.0f)) * x * x + 1.0f;
+    if (x < 2.0f) return (((x - 5.0f) * x + 8.0f) * x - 4.0f) * a;
+    return 0.f;
+  }
+}
+
+template <bool CUBIC>
 __global__ void resize_aa_axis_kernel(const float* __restrict__ x, long long planes, int in_len, int out_len,
                                       long long inner, float scale, float* __restrict__ out) {
   const long long total = planes * out_len * inner;
-  const float support = scale >= 1.0f ? scale : 1.0f;
+  const float half_size = CUBIC ? 2.0f : 1.0f;
+  const float support = scale >= 1.0f ? half_size * scale : half_size;
   const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long in_i = idx % inner;
@@ -262,17 +277,11 @@ __global__ void resize_aa_axis_kernel(const float* __restrict__ x, long long pla
     int xmax = (int)(center + support + 0.5f);
     if (xmax > in_len) xmax = in_len;
     float total_w = 0.f;
-    for (int j = xmin; j < xmax; ++j) {
-      const float a = fabsf(((float)j - center + 0.5f) * invscale);
-      total_w += a < 1.0f ? 1.0f - a : 0.f;
-    }
+    for (int j = xmin; j < xmax; ++j) total_w += aa_filter<CUBIC>(((float)j - center + 0.5f) * invscale);
     const float* src = x + pl * in_len * inner + in_i;
     float acc = 0.f;
-    for (int j = xmin; j < xmax; ++j) {
-      const float a = fabsf(((float)j - center + 0.5f) * invscale);
-      const float w = (a < 1.0f ? 1.0f - a : 0.f) / total_w;
-      acc += w * src[(long long)j * inner];
-    }
+    for (int j = xmin; j < xmax; ++j)
+      acc += (aa_filter<CUBIC>(((float)j - center + 0.5f) * invscale) / total_w) * src[(long long)j * inner];
     out[idx] = acc;
   }
 }
@@ -390,9 +399,20 @@ extern "C" int b200_resize_bilinear_aa(const float* x, long long planes, int H, 
                  "b200_resize_bilinear_aa: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   // width pass [planes*H][W] -> tmp [planes*H][OW], then height pass [planes][H][OW] -> out [planes][OH][OW]
-  resize_aa_axis_kernel<<<pp_grid(planes * H * OW, 1), 256, 0, st>>>(x, planes * H, W, OW, 1, (float)W / (float)OW, tmp);
-  resize_aa_axis_kernel<<<pp_grid(planes * OH * OW, 1), 256, 0, st>>>(tmp, planes, H, OH, OW, (float)H / (float)OH, out);
+  resize_aa_axis_kernel<false><<<pp_grid(planes * H * OW, 1), 256, 0, st>>>(x, planes * H, W, OW, 1, (float)W / (float)OW, tmp);
+  resize_aa_axis_kernel<false><<<pp_grid(planes * OH * OW, 1), 256, 0, st>>>(tmp, planes, H, OH, OW, (float)H / (float)OH, out);
   B200_CHECK_LAUNCH("resize_aa_axis_kernel");
+  return 0;
+}
+
+extern "C" int b200_resize_bicubic_aa(const float* x, long long planes, int H, int W, int OH, int OW, float* tmp,
+                                      float* out, void* stream) {
+  B200_CHECK_ARG(x && tmp && out && planes > 0 && H > 0 && W > 0 && OH > 0 && OW > 0,
+                 "b200_resize_bicubic_aa: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  resize_aa_axis_kernel<true><<<pp_grid(planes * H * OW, 1), 256, 0, st>>>(x, planes * H, W, OW, 1, (float)W / (float)OW, tmp);
+  resize_aa_axis_kernel<true><<<pp_grid(planes * OH * OW, 1), 256, 0, st>>>(tmp, planes, H, OH, OW, (float)H / (float)OH, out);
+  B200_CHECK_LAUNCH("resize_aa_axis_kernel<cubic>");
   return 0;
 }
 

@@ -77,7 +77,12 @@ def normalise_rgb(rgb: torch.Tensor, round_u8=False):
     return out
 
 
-def resize_bilinear_aa(x: torch.Tensor, size):
+def resize_bicubic_aa(x: torch.Tensor, size):
+    """torchvision `resize(x, size, BICUBIC, antialias=True)` of a [..., H, W] CUDA tensor (geowizard_pipeline.py:239-243)."""
+    return resize_bilinear_aa(x, size, _fn="b200_resize_bicubic_aa")
+
+
+def resize_bilinear_aa(x: torch.Tensor, size, _fn="b200_resize_bilinear_aa"):
     """torchvision `resize(x, size, BILINEAR, antialias=True)` of a [..., H, W] fp32 CUDA tensor."""
     _need_cuda(x)
     xf = x.to(F32).contiguous()
@@ -86,8 +91,7 @@ def resize_bilinear_aa(x: torch.Tensor, size):
     planes = xf.numel() // (H * W)
     tmp = torch.empty((planes, H, OW), dtype=F32, device=x.device)
     out = torch.empty((*xf.shape[:-2], OH, OW), dtype=F32, device=x.device)
-    _ck(_lib.load().b200_resize_bilinear_aa(_p(xf), planes, H, W, OH, OW, _p(tmp), _p(out), _stream()),
-        "b200_resize_bilinear_aa")
+    _ck(getattr(_lib.load(), _fn)(_p(xf), planes, H, W, OH, OW, _p(tmp), _p(out), _stream()), _fn)
     return out
 
 

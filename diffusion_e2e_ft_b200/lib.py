@@ -79,6 +79,7 @@ _SIGS = {
     "b200_minmax_normalise": (c_int, [_P, _LL, _P, _P, _P]),
     "b200_rgb_normalise": (c_int, [_P, c_int, _LL, c_int, _P, _P]),
     "b200_resize_bilinear_aa": (c_int, [_P, _LL, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "b200_resize_bicubic_aa": (c_int, [_P, _LL, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "b200_resize_nearest": (c_int, [_P, _LL, c_int, c_int, c_int, c_int, _P, _P]),
     "b200_cast_f32_to_f16": (c_int, [_P, _P, _LL, _P]),
     "b200_nhwc_to_nchw_f32": (c_int, [_P, c_int, c_int, c_int, _LL, _P, _P]),

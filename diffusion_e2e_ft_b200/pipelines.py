@@ -350,8 +350,9 @@ class DepthNormalPipelineOutput:
 
 
 class DepthNormalEstimationPipeline(PipelineBase):
-    """GeoWizard joint depth+normal pipeline (geowizard_pipeline.py).  The CLIP image encoder is not
-    available offline: pass `img_embed` ([B or 1, 1, 768]) or an `image_encoder` callable."""
+    """GeoWizard joint depth+normal pipeline (geowizard_pipeline.py).  The image context comes from `image_encoder`
+    (clip_vision.B200CLIPVisionModelWithProjection, or any object with the transformers interface) through
+    `encode_img_embed` (:232-248), or is passed in as `img_embed` ([B or 1, 1, 768])."""
 
     latent_scale_factor = 0.18215
 
@@ -381,8 +382,10 @@ class DepthNormalEstimationPipeline(PipelineBase):
         geo_latent = torch.zeros_like(rgb_latent).repeat(2, 1, 1, 1)
         rgb_latent = rgb_latent.repeat(2, 1, 1, 1)
         emb = img_embed if img_embed is not None else self.img_embed
+        if emb is None and self.image_encoder is not None:
+            emb = self.encode_img_embed(input_rgb)
         if emb is None:
-            raise RuntimeError("no CLIP image encoder offline: pass img_embed ([B or 1,1,768])")
+            raise RuntimeError("no image_encoder registered: pass img_embed ([B or 1,1,768])")
         ctx = emb.to(device)
         ctx = ctx.repeat(2, 1, 1) if ctx.shape[0] == B else ctx.repeat(2 * B, 1, 1)
         cls = self.class_embedding(domain, B, device, rgb_latent.dtype)
@@ -396,6 +399,17 @@ class DepthNormalEstimationPipeline(PipelineBase):
         depth = ops.decode_post(d.float().contiguous(), normals=False).to(d.dtype)
         normal = ops.decode_post(n.float().contiguous(), normals=True, sign=-1.0).to(n.dtype)   # :342 sign flip
         return depth, normal
+
+    @torch.no_grad()
+    def encode_img_embed(self, rgb):
+        """geowizard_pipeline.py:232-248: bicubic-antialiased resize of (rgb + 1) / 2 to the crop size, CLIP mean / std,
+        image_encoder(...).image_embeds.unsqueeze(1) -> [B, 1, 768] (one context row per input image)."""
+        enc = self.image_encoder
+        if hasattr(enc, "preprocess"):                                    # the engine encoder: device kernels
+            x = enc.preprocess(rgb.float().contiguous(), self.feature_extractor)
+        else:
+            raise RuntimeError("image_encoder has no device `preprocess`; use B200CLIPVisionModelWithProjection or pass img_embed")
+        return enc(x.to(enc.dtype)).image_embeds.unsqueeze(1).to(self.dtype)
 
     def encode_RGB(self, rgb_in):
         return self.vae.encode_scaled_mean(rgb_in)

@@ -279,6 +279,12 @@ void b200_debug_set_swap(int mode);
 void b200_debug_set_halo(int mode);   /* 1 = automatic halo-resident stride-1 3x3 conv (default), 0 = per-tap boxes */
 int b200_debug_last_path(void);       /* path of the last b200_conv2d_nhwc call: 1 = halo-resident, 0 = per-tap boxes */
 
+/* torchvision resize(x, size, BICUBIC, antialias=True) of [planes][H][W] fp32 (aten _upsample_bicubic2d_aa, Keys
+ * cubic a = -0.5): the CLIP image-encoder input of GeoWizard/geowizard/models/geowizard_pipeline.py:239-243.
+ * tmp: [planes][H][OW] fp32 scratch. */
+int b200_resize_bicubic_aa(const float* x, long long planes, int H, int W, int OH, int OW, float* tmp, float* out,
+                           void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-pipeline post/pre-processing on the device.
  *

@@ -49,7 +49,7 @@ def linear(a, w, bias=None, residual=None, out=None, out_dtype=F16, act=ops.ACT_
         assert a.stride(0) % 8 == 0
     if w.dim() == 3:
         assert w.stride(0) % 8 == 0
-    assert out is None or (out.data_ptr() % 16 == 0 and out.stride(-1) == 1)
+    assert out is None or (out.data_ptr() % 16 == 0 and out.stride(-1) == 1 and out.stride(-2) % 4 == 0)
     af = a.float().transpose(-1, -2) if a_t else a.float()
     wf = w.float() if w_t else w.float().transpose(-1, -2)
     r = af @ wf * alpha

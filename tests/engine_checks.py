@@ -472,3 +472,29 @@ def run_pipeline_with_text_encoder(device="cuda:0"):
     ctx_ref = clip_text_forward(sd, cfg, torch.tensor([[49406, 49407]]))[0]
     want = OP.marigold_single_infer(unet_ref, vae_ref, DDIMOneStep(), rgb, ctx_ref)
     return dict(ctx_rel_l2=rel_l2(pipe.empty_text_embed, ctx_ref), depth_rel_l2=rel_l2(depth, want))
+
+
+@torch.no_grad()
+def run_geowizard_with_image_encoder(device="cuda:0"):
+    """geowizard_pipeline.py:232-248,283-288 on the engine: rgb -> bicubic-AA resize + CLIP normalisation ->
+    B200CLIPVisionModelWithProjection -> img_embed [B,1,proj] -> the joint depth+normal step; against the oracle image
+    encoder feeding the oracle GeoWizard step."""
+    from diffusion_e2e_ft_b200 import B200CLIPVisionModelWithProjection, CLIPImageProcessorConfig
+    from oracle.clip_vision import geowizard_img_embed, random_vision_state_dict, tiny_vision_cfg
+    from oracle.pipeline import DDIMOneStep
+    unet_ref, vae_ref = MG.build_tiny("geowizard")
+    unet, vae = engine_from_oracle(unet_ref, vae_ref, device)
+    cfg = tiny_vision_cfg(projection_dim=unet_ref.config.cross_attention_dim)
+    sd = random_vision_state_dict(cfg, seed=23)
+    enc = B200CLIPVisionModelWithProjection(
+        hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_hidden_layers,
+        num_attention_heads=cfg.num_attention_heads, image_size=cfg.image_size, projection_dim=cfg.projection_dim).eval()
+    enc.load_state_dict(sd)
+    pipe = DepthNormalEstimationPipeline(unet, vae, DDIMScheduler(),
+                                         image_encoder=enc.to(device), feature_extractor=CLIPImageProcessorConfig(cfg.image_size))
+    rgb = (torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(3)) * 2 - 1)
+    depth, normal = pipe.single_infer(rgb.to(device), 1, "indoor")
+    emb_ref = geowizard_img_embed(sd, cfg, rgb)
+    want_d, want_n = OP.geowizard_single_infer(unet_ref, vae_ref, DDIMOneStep(), rgb, emb_ref, domain="indoor")
+    return dict(img_embed_rel_l2=rel_l2(pipe.encode_img_embed(rgb.to(device)), emb_ref),
+                depth_rel_l2=rel_l2(depth, want_d), normal_angle_deg=mean_angle_deg(normal, want_n))

@@ -69,13 +69,19 @@ def test_state_dict_names_are_transformers_names():
     with pytest.raises(NotImplementedError):
         B200CLIPTextModel(hidden_size=768, num_attention_heads=8)            # head width 96
     with pytest.raises(NotImplementedError):
-        B200CLIPTextModel(hidden_act="quick_gelu")
+        B200CLIPTextModel(hidden_act="relu")
 
 
 def test_host_logic_on_cpu_emulation(monkeypatch, tmp_path):
     import cpu_emulation
     from diffusion_e2e_ft_b200 import B200CLIPTextModel, EmptyPromptTokenizer, MarigoldPipeline
     cpu_emulation.install(monkeypatch)
+    qcfg = tiny_clip_cfg(hidden_act="quick_gelu")                      # SD-1.x text encoders: SiLU epilogue on 1.702-scaled fc1
+    qsd = random_state_dict(qcfg, seed=6)
+    q = B200CLIPTextModel(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                          hidden_act="quick_gelu").eval()
+    q.load_state_dict(qsd)
+    assert _rel(q(_ids(2, 5))[0], clip_text_forward(qsd, qcfg, _ids(2, 5))[0]) <= 3e-3
     cfg = tiny_clip_cfg()
     sd = random_state_dict(cfg, seed=5)
     eng = B200CLIPTextModel(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2).eval()
