@@ -230,7 +230,13 @@ def build_engine(device, stream_dtype, module_dtype, workload="marigold", seed=1
     unet.to(module_dtype).eval().requires_grad_(False)
     vae.to(module_dtype).eval().requires_grad_(False)
     if workload == "geowizard":
-        return DepthNormalEstimationPipeline(unet, vae, DDIMScheduler())
+        # geowizard_pipeline.py:232-248,283-288: the CLIP ViT-L/14 image encoder runs for every input image
+        from diffusion_e2e_ft_b200 import B200CLIPVisionModelWithProjection, CLIPImageProcessorConfig
+        with torch.device(device):
+            enc = B200CLIPVisionModelWithProjection()
+        enc.to(module_dtype).eval().requires_grad_(False)
+        return DepthNormalEstimationPipeline(unet, vae, DDIMScheduler(), image_encoder=enc,
+                                             feature_extractor=CLIPImageProcessorConfig(224))
     ete = (torch.randn(1, 2, 1024, device=device) * 0.5).to(module_dtype)
     return MarigoldPipeline(unet, vae, DDIMScheduler(), empty_text_embed=ete)
 
@@ -392,11 +398,10 @@ def run_engine(args):
     out_ch = {"marigold": 1, "normals": 3, "geowizard": 4}[wl]
     host_out = torch.empty(bs, out_ch, res, res, dtype=torch.float32).pin_memory()
     dev_rgb = host_rgb.to(dev)
-    emb = (torch.randn(bs, 1, 768, device=dev) * 0.5).half() if wl == "geowizard" else None
 
     def infer(x):
         if wl == "geowizard":
-            d, n = pipe.single_infer(x, 1, "indoor", img_embed=emb)
+            d, n = pipe.single_infer(x, 1, "indoor")       # resize + CLIP image encoder + VAE + joint UNet + 2 decodes
             return torch.cat([d, n], 1)
         return pipe.single_infer(x, 1, False, noise="zeros", normals=(wl == "normals"))
 
@@ -535,7 +540,7 @@ def run_engine(args):
                           f"{tj.get('algorithmic_bytes_min', 0) / 1e9:.3f} GB ({tj.get('source')})")
         names = {"marigold": ("marigold-e2e-ft-depth single_infer", "BASELINE.json configs[1]"),
                  "normals": ("marigold-e2e-ft-normals single_infer", "BASELINE.json configs[4]"),
-                 "geowizard": ("geowizard-e2e-ft joint depth+normals single_infer (indoor)", "BASELINE.json configs[3]")}[wl]
+                 "geowizard": ("geowizard-e2e-ft joint depth+normals single_infer (indoor), CLIP ViT-L/14 image encoder per image included", "BASELINE.json configs[3]")}[wl]
         out = {
             "metric": METRIC if (wl == "marigold" and res == 768) else f"images_per_sec_{res}x{res}_{wl}",
             "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,

@@ -207,8 +207,10 @@ class B200CLIPVisionModelWithProjection(nn.Module):
         fe = feature_extractor or CLIPImageProcessorConfig(self.config["image_size"])
         size = (fe.crop_size["height"], fe.crop_size["width"])
         x = resize_bicubic_aa(rgb, size)
-        std = torch.tensor(fe.image_std, dtype=F32)
-        mean = torch.tensor(fe.image_mean, dtype=F32)
-        wm = torch.diag(0.5 / std).to(rgb.device)
-        bias = ((0.5 - mean) / std).to(rgb.device)
-        return ops.pointwise_nchw(x, 1.0, wm, bias)
+        key = (str(rgb.device), tuple(fe.image_mean), tuple(fe.image_std))
+        cache = self.__dict__.setdefault("_affine", {})
+        if key not in cache:                                             # once per device: no per-image host->device copy
+            std = torch.tensor(fe.image_std, dtype=F32)
+            mean = torch.tensor(fe.image_mean, dtype=F32)
+            cache[key] = (torch.diag(0.5 / std).to(rgb.device), ((0.5 - mean) / std).to(rgb.device))
+        return ops.pointwise_nchw(x, 1.0, *cache[key])
