@@ -233,7 +233,10 @@ static int gn_block(int C) {
 
 // ------------------------------------------------------------------------------ LayerNorm
 // one warp per row; C <= 2048, C % 8 == 0.  Two-pass in registers (exact mean, then variance).
-template <typename T>
+// NV = per-lane 8-element vectors actually needed (ceil(C / 256)) is a template parameter: with the fixed 8 (64 value
+// registers, most of them dead for C = 320 / 640) the kernel ran 2 CTAs per SM and kept ~20 KB in flight per SM — 29 %
+// of the HBM roofline (r2 bench: 1.96 ms / step for 3.7 GB).
+template <typename T, int NV>
 __global__ void layer_norm_kernel(const T* __restrict__ x, long long rows, int C,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   float eps, __half* __restrict__ y) {
@@ -241,12 +244,11 @@ __global__ void layer_norm_kernel(const T* __restrict__ x, long long rows, int C
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int V = C / 8;
-  constexpr int kMaxV = 8;   // per-lane vectors: C <= 32*8*8 = 2048
-  float f[kMaxV][8];
+  float f[NV][8];
   float s = 0.f;
   const T* xr = x + row * C;
 #pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
     if (v < V) {
       load8(xr + v * 8, f[i]);
@@ -257,7 +259,7 @@ __global__ void layer_norm_kernel(const T* __restrict__ x, long long rows, int C
   const float mean = warp_sum(s) / C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
     if (v < V) {
 #pragma unroll
@@ -267,7 +269,7 @@ __global__ void layer_norm_kernel(const T* __restrict__ x, long long rows, int C
   const float rstd = rsqrtf(warp_sum(q) / C + eps);
   __half* yr = y + row * C;
 #pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
     if (v < V) {
       float g[8], b[8], o[8];
@@ -277,6 +279,23 @@ __global__ void layer_norm_kernel(const T* __restrict__ x, long long rows, int C
       for (int e = 0; e < 8; ++e) o[e] = (f[i][e] - mean) * rstd * g[e] + b[e];
       store8h(yr + v * 8, o);
     }
+  }
+}
+
+template <typename T>
+static void launch_layer_norm(const T* x, long long rows, int C, const float* gamma, const float* beta, float eps,
+                              __half* y, cudaStream_t st) {
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  switch ((C + 255) / 256) {
+    case 1: layer_norm_kernel<T, 1><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, y); break;
+    case 2: layer_norm_kernel<T, 2><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, y); break;
+    case 3: layer_norm_kernel<T, 3><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, y); break;
+    case 4: layer_norm_kernel<T, 4><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, y); break;
+    case 5: layer_norm_kernel<T, 5><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, y); break;
+    case 6: layer_norm_kernel<T, 6><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, y); break;
+    case 7: layer_norm_kernel<T, 7><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, y); break;
+    default: layer_norm_kernel<T, 8><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, y); break;
   }
 }
 
@@ -338,49 +357,83 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, 
 }
 
 // Same result, one HBM read per row: the fp32 row is staged in shared memory (cols <= 16384) and the max / sum / write
-// passes run out of it.  The three-pass kernel above re-read a 36 KB row from L2 twice and sat at 30 % of the HBM
-// roofline (r2 bench: 2.1 ms / step for the VAE's two 9216 x 9216 score matrices per image).
+// passes run out of it.  Persistent CTAs; the rows arrive by cp.async.bulk (one elected thread, no register staging)
+// into a two-deep ring, so the next row is in flight while this one is reduced and written — with register-staged
+// loads issued by the same threads that later do the exp / store passes the kernel kept ~35 KB in flight per SM and sat
+// at 59 % of the HBM roofline (r2 bench: 2.1 ms / step for the VAE's two 9216 x 9216 score matrices per image).
+__device__ __forceinline__ void bulk_load_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __global__ void softmax_rows_smem_kernel(const float* __restrict__ S, long long lds, __half* __restrict__ P,
-                                         long long ldp, int cols, float scale) {
-  extern __shared__ float row[];
+                                         long long ldp, long long rows, int cols, float scale) {
+  extern __shared__ __align__(16) float rowbuf[];          // [2][cols]
   __shared__ float red[32];
-  const float* s = S + (long long)blockIdx.x * lds;
-  __half* p = P + (long long)blockIdx.x * ldp;
+  __shared__ __align__(8) uint64_t full[2];
   const int tid = threadIdx.x, nw = blockDim.x >> 5;
-  float m = -INFINITY;
-  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(s + c);
-    *reinterpret_cast<float4*>(row + c) = v;
-    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  const uint32_t row_bytes = (uint32_t)cols * 4u;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
   }
-  m = warp_max(m);
-  if ((tid & 31) == 0) red[tid >> 5] = m;
   __syncthreads();
-  m = red[0];
-  for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
-  __syncthreads();
+  long long r = blockIdx.x;
+  if (tid == 0 && r < rows) {
+    mbar_arrive_expect_tx(&full[0], row_bytes);
+    bulk_load_row(rowbuf, S + r * lds, row_bytes, &full[0]);
+  }
   const float sl2 = scale * 1.4426950408889634f;
-  const float ms = m * sl2;
-  float sum = 0.f;
-  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {      // each thread re-reads exactly what it wrote
-    float4 v = *reinterpret_cast<const float4*>(row + c);
-    v.x = exp2f(v.x * sl2 - ms); v.y = exp2f(v.y * sl2 - ms); v.z = exp2f(v.z * sl2 - ms); v.w = exp2f(v.w * sl2 - ms);
-    *reinterpret_cast<float4*>(row + c) = v;
-    sum += (v.x + v.y) + (v.z + v.w);
-  }
-  sum = warp_sum(sum);
-  if ((tid & 31) == 0) red[tid >> 5] = sum;
-  __syncthreads();
-  sum = 0.f;
-  for (int i = 0; i < nw; ++i) sum += red[i];
-  const float inv = 1.0f / sum;
-  for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row + c);
-    __half2 a = __floats2half2_rn(v.x * inv, v.y * inv), b = __floats2half2_rn(v.z * inv, v.w * inv);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p + c) = u;
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;
+  for (; r < rows; r += gridDim.x, buf ^= 1) {
+    const long long rn = r + gridDim.x;
+    if (tid == 0 && rn < rows) {
+      // the other buffer was last touched by generic-proxy stores of the previous iteration (all threads are past the
+      // trailing __syncthreads): order them before the async-proxy write
+      fence_proxy_async_smem();
+      mbar_arrive_expect_tx(&full[buf ^ 1], row_bytes);
+      bulk_load_row(rowbuf + (size_t)(buf ^ 1) * cols, S + rn * lds, row_bytes, &full[buf ^ 1]);
+    }
+    mbar_wait(&full[buf], phase[buf]);
+    phase[buf] ^= 1u;
+    float* row = rowbuf + (size_t)buf * cols;
+    __half* p = P + r * ldp;
+    float m = -INFINITY;
+    for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    m = warp_max(m);
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    const float ms = m * sl2;
+    float sum = 0.f;
+    for (int c = tid * 4; c < cols; c += blockDim.x * 4) {      // each thread re-reads exactly what it writes
+      float4 v = *reinterpret_cast<const float4*>(row + c);
+      v.x = exp2f(v.x * sl2 - ms); v.y = exp2f(v.y * sl2 - ms); v.z = exp2f(v.z * sl2 - ms); v.w = exp2f(v.w * sl2 - ms);
+      *reinterpret_cast<float4*>(row + c) = v;
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+    sum = warp_sum(sum);
+    if ((tid & 31) == 0) red[tid >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int i = 0; i < nw; ++i) sum += red[i];
+    const float inv = 1.0f / sum;
+    for (int c = tid * 4; c < cols; c += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      __half2 a = __floats2half2_rn(v.x * inv, v.y * inv), b = __floats2half2_rn(v.z * inv, v.w * inv);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(p + c) = u;
+    }
+    __syncthreads();                                          // `red` and this row buffer are free again
   }
 }
 
@@ -509,13 +562,11 @@ extern "C" int b200_layer_norm(const void* x, int in_f32, long long rows, int C,
                                const float* beta, float eps, void* y, void* stream) {
   B200_CHECK_ARG(x && y && gamma && beta && rows > 0, "b200_layer_norm: bad arguments");
   B200_CHECK_ARG(C % 8 == 0 && C <= 2048, "b200_layer_norm: C=%d must be a multiple of 8 and <= 2048", C);
-  const int wpb = 8;
-  const long long grid = (rows + wpb - 1) / wpb;
   cudaStream_t st = (cudaStream_t)stream;
   if (in_f32)
-    layer_norm_kernel<float><<<(unsigned)grid, wpb * 32, 0, st>>>((const float*)x, rows, C, gamma, beta, eps, (__half*)y);
+    launch_layer_norm<float>((const float*)x, rows, C, gamma, beta, eps, (__half*)y, st);
   else
-    layer_norm_kernel<__half><<<(unsigned)grid, wpb * 32, 0, st>>>((const __half*)x, rows, C, gamma, beta, eps, (__half*)y);
+    launch_layer_norm<__half>((const __half*)x, rows, C, gamma, beta, eps, (__half*)y, st);
   B200_CHECK_LAUNCH("layer_norm_kernel");
   return 0;
 }
@@ -529,10 +580,14 @@ extern "C" int b200_softmax_rows(const float* S, long long lds, void* P, long lo
     const int dev_ = current_device();
     bool& configured = configured_dev[dev_ < 0 ? 0 : dev_];
     if (!configured || dev_ < 0) {
-      cudaFuncSetAttribute(softmax_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+      cudaFuncSetAttribute(softmax_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536);
       configured = true;
     }
-    softmax_rows_smem_kernel<<<(unsigned)rows, 256, (size_t)cols * 4, (cudaStream_t)stream>>>(S, lds, (__half*)P, ldp, cols, scale);
+    const size_t smem = (size_t)cols * 8;                         // two row buffers
+    const long long per_sm = (220 * 1024) / (long long)(smem + 1024);
+    long long grid = (long long)sm_count() * (per_sm < 1 ? 1 : per_sm);
+    if (grid > rows) grid = rows;
+    softmax_rows_smem_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(S, lds, (__half*)P, ldp, rows, cols, scale);
   } else if (vec)
     softmax_rows_kernel<4><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(S, lds, (__half*)P, ldp, cols, scale);
   else

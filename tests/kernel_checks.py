@@ -732,6 +732,15 @@ CHECKS = {
     "ln_f16_1280": lambda: check_layer_norm(C=1280, in_f32=False),
     "ln_320": lambda: check_layer_norm(C=320),
     "softmax_rows": check_softmax_rows,
+    "softmax_rows_persistent_9216": lambda: check_softmax_rows(rows=2100, cols=9216, seed=1),   # ~7 rows per CTA, 2-deep ring
+    "softmax_rows_persistent_1024": lambda: check_softmax_rows(rows=9001, cols=1024, seed=2),
+    "softmax_rows_single_row": lambda: check_softmax_rows(rows=1, cols=64, seed=3),
+    "softmax_rows_16384": lambda: check_softmax_rows(rows=333, cols=16384, seed=4),
+    "softmax_rows_unaligned_cols": lambda: check_softmax_rows(rows=50, cols=77, seed=5),         # scalar fallback kernel
+    "ln_8": lambda: check_layer_norm(rows=77, C=8),
+    "ln_1024": lambda: check_layer_norm(rows=514, C=1024),
+    "ln_2048_f16": lambda: check_layer_norm(rows=300, C=2048, in_f32=False),
+    "ln_1536": lambda: check_layer_norm(rows=300, C=1536),
     "attn_self_576": lambda: check_attention(),
     "attn_self_2304": lambda: check_attention(B=1, heads=10, Lq=2304),
     "attn_ragged_144": lambda: check_attention(B=2, heads=20, Lq=144),

@@ -52,6 +52,15 @@ elif what == "lin320":                # K = 320 GEMM with fp32 residual / output
     resid = r(73728, 320).float()
     fn = lambda: ops.linear(a, w, b, residual=resid, out_dtype=torch.float32)
     flops = 2 * 73728 * 320 * 320
+elif what.startswith("ln"):            # ln320 / ln640 / ln1280: the UNet's LayerNorms, fp32 stream in, fp16 out (6 B / element)
+    C = int(what[2:]); rows = {320: 73728, 640: 18432, 1280: 4608}[C] * (8 if C != 320 else 1)
+    x = r(rows, C).float(); gm = torch.ones(C, device=dev); bt = torch.zeros(C, device=dev)
+    fn = lambda: ops.layer_norm(x, gm, bt)
+    flops = 0; nbytes = rows * C * 6
+elif what == "softmax":               # the VAE attention's score matrix of 2 images: fp32 in, fp16 out
+    sm = r(2 * 9216, 9216).float()
+    fn = lambda: ops.softmax_rows(sm, 0.044)
+    flops = 0; nbytes = 2 * 9216 * 9216 * 6
 elif what == "geglu":
     pass
 elif what == "linear":
@@ -72,4 +81,4 @@ for _ in range(reps):
     fn()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-print(f"{what}: {ms:.3f} ms/iter  {flops / ms / 1e9:.1f} TFLOP/s")
+print(f"{what}: {ms:.3f} ms/iter  {flops / ms / 1e9:.1f} TFLOP/s" + (f"  {nbytes / ms / 1e6:.0f} GB/s" if "nbytes" in dir() else ""))
