@@ -22,6 +22,7 @@ _SIGS = {
     "b200_debug_set_flags": (None, [c_int]),
     "b200_debug_set_swap": (None, [c_int]),
     "b200_debug_set_halo": (None, [c_int]),
+    "b200_debug_set_attention_version": (None, [c_int]),
     "b200_debug_last_path": (c_int, []),
     "b200_geglu_block_n": (c_int, [c_int]),
     "b200_linear": (c_int, [_P, _LL, _LL, _P, _LL, _LL, c_int, c_int, c_int, c_int, _P, c_int, _P, _LL, _LL,

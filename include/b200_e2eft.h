@@ -277,6 +277,7 @@ void b200_debug_set_flags(int flags);
 /* 1 (default) = swap operands automatically when Cout % 128 == 0; 0 = never */
 void b200_debug_set_swap(int mode);
 void b200_debug_set_halo(int mode);   /* 1 = automatic halo-resident stride-1 3x3 conv (default), 0 = per-tap boxes */
+void b200_debug_set_attention_version(int v);      /* 2 = two-pass softmax, O in registers; 3 = S read once, O in TMEM */
 int b200_debug_last_path(void);       /* path of the last b200_conv2d_nhwc call: 1 = halo-resident, 0 = per-tap boxes */
 
 /* torchvision resize(x, size, BICUBIC, antialias=True) of [planes][H][W] fp32 (aten _upsample_bicubic2d_aa, Keys

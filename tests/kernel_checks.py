@@ -435,7 +435,27 @@ def check_softmax_rows(rows=300, cols=1152, seed=0):
 
 
 # ----------------------------------------------------------------------------------- attention
-def check_attention(B=2, heads=5, Lq=576, Lk=None, joint=False, gain=3.0, seed=0):
+def _attention_version(v):
+    from diffusion_e2e_ft_b200 import lib as _l
+    _l.load().b200_debug_set_attention_version(v)
+
+
+def with_attention_version(fn, version=2):
+    """Run an attention check on the other flash kernel: 3 (default) = attention_d64_v3_kernel (S read once, O accumulated
+    in TMEM, lazy rescale), 2 = the two-pass kernel with O in registers (kept selectable: b200_debug_set_attention_version)."""
+    def run():
+        _attention_version(version)
+        try:
+            return fn()
+        finally:
+            _attention_version(ATTENTION_DEFAULT_VERSION)
+    return run
+
+
+ATTENTION_DEFAULT_VERSION = 3
+
+
+def check_attention(B=2, heads=5, Lq=576, Lk=None, joint=False, gain=3.0, seed=0, ramp=None):
     Lk = Lk or Lq
     C = heads * 64
     qkv = _rand(B, Lq, 3 * C, seed=seed)
@@ -445,6 +465,12 @@ def check_attention(B=2, heads=5, Lq=576, Lk=None, joint=False, gain=3.0, seed=0
         q = qkv[..., :C]
         kv = _rand(B, Lk, 2 * C, seed=seed + 1)
         k, v = kv[..., :C], kv[..., C:]
+    if ramp is not None:
+        # key magnitude grows (ramp > 0) or shrinks (< 0) along the sequence: the running row maximum keeps moving, by
+        # more AND by less than the lazy-rescale threshold of the v3 kernel (2^8), tile after tile
+        r = torch.linspace(0.05, abs(ramp), Lk, device=DEV)
+        r = r if ramp > 0 else r.flip(0)
+        k = (k.float() * r[None, :, None]).half()
     q = q * gain if False else q
     scale = 64 ** -0.5 * gain
     out = ops.attention_d64(q, k, v, heads, scale, kv_segments=2 if joint else 1)
@@ -748,6 +774,18 @@ CHECKS = {
     "attn_cross_77": lambda: check_attention(Lq=300, Lk=77),
     "attn_joint": lambda: check_attention(B=4, heads=5, Lq=576, joint=True),
     "attn_lse_rowdot_exp2_gemm": check_attention_lse_and_rowdot,
+    "attn_ramp_up": lambda: check_attention(B=1, heads=3, Lq=700, Lk=1500, ramp=6.0),
+    "attn_ramp_down": lambda: check_attention(B=1, heads=3, Lq=700, Lk=1500, ramp=-6.0),
+    "attn_v2_self_576": with_attention_version(lambda: check_attention()),
+    "attn_v2_self_2304": with_attention_version(lambda: check_attention(B=1, heads=10, Lq=2304)),
+    "attn_v2_ragged_144": with_attention_version(lambda: check_attention(B=2, heads=20, Lq=144)),
+    "attn_v2_cross_2": with_attention_version(lambda: check_attention(Lq=576, Lk=2)),
+    "attn_v2_cross_77": with_attention_version(lambda: check_attention(Lq=300, Lk=77)),
+    "attn_v2_joint": with_attention_version(lambda: check_attention(B=4, heads=5, Lq=576, joint=True)),
+    "attn_v2_lse_rowdot_exp2_gemm": with_attention_version(check_attention_lse_and_rowdot),
+    "attn_v2_ramp_up": with_attention_version(lambda: check_attention(B=1, heads=3, Lq=700, Lk=1500, ramp=6.0)),
+    "attn_v2_ramp_down": with_attention_version(lambda: check_attention(B=1, heads=3, Lq=700, Lk=1500, ramp=-6.0)),
+    "attn_v2_single_query": with_attention_version(lambda: check_attention(B=2, heads=4, Lq=1, Lk=9)),
     "upsample_2x": check_upsample,
     "upsample_size_f32": lambda: check_upsample(True, (15, 20)),
     "timestep_embedding": check_timestep_embedding,

@@ -14,6 +14,8 @@ if len(sys.argv) > 4:
     _l.load().b200_debug_force_block_n(int(sys.argv[4]))
 if len(sys.argv) > 5:
     _l.load().b200_debug_set_swap(int(sys.argv[5]))
+if os.environ.get("B200_ATT_VERSION"):
+    _l.load().b200_debug_set_attention_version(int(os.environ["B200_ATT_VERSION"]))
 if os.environ.get("B200_HALO"):
     _l.load().b200_debug_set_halo(int(os.environ["B200_HALO"]))
 dev = "cuda"
@@ -35,6 +37,10 @@ elif what.startswith("res"):          # res16 / res32: 128->128 768^2 conv with 
     resid = r(NB, H, W, Cout).to(odt)
     fn = lambda: ops.conv2d(x, w, Cout, bias=b, residual=resid, out_dtype=odt)
     flops = 2 * NB * H * W * Cout * 9 * Cin
+elif what == "attn2304":             # level-1 self-attention: 10 heads, 2304 tokens
+    qkv = r(8, 2304, 1920)
+    fn = lambda: ops.attention_d64(qkv[..., :640], qkv[..., 640:1280], qkv[..., 1280:], 10, 0.125)
+    flops = 4 * 8 * 10 * 2304 * 2304 * 64
 elif what == "attn":
     qkv = r(8, 9216, 960)
     fn = lambda: ops.attention_d64(qkv[..., :320], qkv[..., 320:640], qkv[..., 640:], 5, 0.125)
