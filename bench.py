@@ -517,6 +517,7 @@ def run_engine(args):
             fms = timed(step_resident, args.steps)
             fast = {"stream_dtype": "fp16", "value": bs * world * args.steps / (fms / 1e3), "ms_per_step": fms / args.steps}
             pipe = pipe_keep
+            fpipe.__dict__.pop("_graphs", None)     # graph entries hold closures over the pipeline (reference cycle)
             del fpipe
         except Exception as e:  # noqa: BLE001
             fast = {"error": repr(e)[:200]}
@@ -576,13 +577,23 @@ def run_engine(args):
     # process with its own process group (MASTER_PORT + 1): a fault or a stuck collective in the training leg can then
     # never take the headline line down with it — the child is killed by PID after the timeout and its error recorded.
     if wl == "marigold" and not args.no_train:
+        # release EVERYTHING this process holds on the GPU first: the child peaks at ~93 GB, and captured graphs keep their
+        # private pools (tens of GB of activations) alive through reference cycles until the cyclic GC runs — a child
+        # squeezed by the parent's leftovers spends its step in allocator retries (observed: 160 -> 240 -> 425 ms)
+        import gc
+        pipe.__dict__.pop("_graphs", None)
         del pipe
+        infer = step_resident = step_e2e = None     # closures over the pipeline
+        gc.collect()
         torch.cuda.empty_cache()
+        free_b, total_b = torch.cuda.mem_get_info(dev)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         t = _train_subprocess(world, rank, local)
         if rank == 0:
+            if isinstance(t, dict):
+                t["gpu_free_gb_at_start"] = free_b / 2 ** 30
             out["train_step"] = t
         world_pg = False
     else:
