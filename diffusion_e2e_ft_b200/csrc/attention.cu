@@ -352,10 +352,9 @@ attention_d64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 // exp pass through named barriers (-2..-6 %: a lone warp per sub-partition cannot saturate the MUFU), two threads per
 // query row = 16 softmax warps (-2 %), a share of the exponentials as an FMA-pipe cubic (-4..-7 %), P V issued in two
 // 64-key halves so that the next tile never waits for it (-8 %).  Every variant lands on ~3000-3300 cycles per pair of
-// tiles: the SS-mode MMAs of this shape already take the whole shared-memory read bandwidth while they run (A 4 KB + B
-// 4 KB per 64-cycle K-step at N = 128, 6 KB per 32 cycles at N = 64), P goes through shared memory as well (64 KB of
-// STS per pair) and the MUFU executes 32768 ex2 + 16384 F2FP packs — three resources at 60-70 % each behind a serial
-// exp -> P V -> exp chain.  The next step is P in TMEM (TS-mode MMA), which removes the P round trip through smem.
+// tiles; ncu of this kernel (profiles/ncu_r02_summary.txt): XU 60 %, issue 41 %, tensor 29 %, shared LSU 16 %, stalls led
+// by `wait` and `long_scoreboard` — a latency-bound serial chain per tile with two softmax warps per scheduler, not a
+// throughput limit.  Untried: P in TMEM (TS-mode MMA), two key tiles in flight per warpgroup.
 // TMEM columns per warpgroup w: S at 256 w, O at 256 w + 128.
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
