@@ -175,3 +175,31 @@ def test_save_pretrained_from_pretrained_round_trip(tmp_path):
     v2 = B200AutoencoderKL.from_pretrained(str(d / "vae"), torch_dtype=torch.float16)
     assert v2.dtype == torch.float16 and v2.config["block_out_channels"] == (64, 64, 128, 128)
     assert torch.equal(v2.state_dict()["decoder.conv_in.weight"], vae.state_dict()["decoder.conv_in.weight"].half())
+
+
+def test_product_package_never_imports_the_oracle():
+    """Tier rule: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/ — the product path has
+    no CPU fallback to route through.  Static check of every module of the package, plus bench.py's engine path."""
+    import ast
+    pkg = os.path.join(ROOT, "diffusion_e2e_ft_b200")
+    for name in sorted(os.listdir(pkg)):
+        if not name.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, name)).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), (name, mods)
+    # bench.py: `oracle` may only be imported inside the CPU-leg functions
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").startswith("oracle"):
+                assert any(k in fn.name for k in ("oracle", "cpu", "reference")), fn.name    # the CPU legs' helpers only
+    for node in tree.body:                                    # and never at module level
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mods = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
+            assert not any(m.startswith("oracle") for m in mods)
